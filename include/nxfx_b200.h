@@ -1,0 +1,188 @@
+/*
+ * nxfx_b200.h -- C ABI of the B200-native hydraulic-network assemble+solve path.
+ *
+ * This is the drop-in boundary for the hot path of scientificcomputing/networks_fenicsx
+ * (NetworkMesh -> HydraulicNetworkAssembler.assemble() -> Solver.solve()).  The reference has no
+ * native code of its own: at these call sites it enters DOLFINx C++ / FFCx kernels / PETSc / MUMPS.
+ * Each entry point below names the reference call site(s) (file:line under
+ * src/networks_fenicsx/) whose native work it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative nxfx_status on failure; the message is
+ *     available from nxfx_last_error(ctx).  Nothing falls back to the CPU.
+ *   - pointers suffixed _h are HOST pointers, _d are DEVICE pointers on the ctx's GPU.
+ *   - the caller owns every buffer it passes in; buffers returned by nxfx_csr_device /
+ *     nxfx_mesh_geometry_device are borrowed views owned by the ctx (valid until the next
+ *     nxfx_set_network / nxfx_destroy).
+ *   - one ctx per GPU per process; a ctx is not thread-safe; all work is enqueued on the ctx's
+ *     stream (nxfx_set_stream, default: the legacy default stream) and is asynchronous unless
+ *     stated otherwise.
+ *   - all reals are IEEE binary64, all indices int32_t (DOLFINx local index width).
+ *
+ * Global unknown order: [flux slots (colour blocks 0..C-1), pressure (one per cell), multipliers
+ * (one per bifurcation)] -- assembly.py:318-321, solver.py:122-125.
+ */
+#ifndef NXFX_B200_H
+#define NXFX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NXFX_ABI_VERSION 1
+
+typedef struct nxfx_ctx nxfx_ctx;
+
+typedef enum {
+  NXFX_OK = 0,
+  NXFX_ERR_INVALID = -1,       /* bad argument / call order */
+  NXFX_ERR_CUDA = -2,          /* CUDA runtime error */
+  NXFX_ERR_NOT_CONVERGED = -3, /* mirrors ksp_error_if_not_converged=True, solver.py:64 */
+  NXFX_ERR_NCCL = -4,
+  NXFX_ERR_UNSUPPORTED = -5
+} nxfx_status;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int nxfx_abi_version(void);
+int nxfx_create(nxfx_ctx** out, int device);
+int nxfx_destroy(nxfx_ctx* ctx);
+const char* nxfx_last_error(const nxfx_ctx* ctx);
+int nxfx_set_stream(nxfx_ctx* ctx, void* cuda_stream); /* cudaStream_t */
+int nxfx_sync(nxfx_ctx* ctx);                          /* cudaStreamSynchronize */
+/* number of kernels this library has launched on ctx since creation (bench.py "gpu_launches") */
+int64_t nxfx_launch_count(const nxfx_ctx* ctx);
+
+/* device / pinned-host memory helpers (PETSc Vec / Mat storage stand-ins) */
+int nxfx_malloc(nxfx_ctx* ctx, size_t bytes, void** out_d);
+int nxfx_free(nxfx_ctx* ctx, void* ptr_d);
+int nxfx_host_alloc(nxfx_ctx* ctx, size_t bytes, void** out_h); /* pinned */
+int nxfx_host_free(nxfx_ctx* ctx, void* ptr_h);
+int nxfx_memcpy_h2d(nxfx_ctx* ctx, void* dst_d, const void* src_h, size_t bytes); /* async */
+int nxfx_memcpy_d2h(nxfx_ctx* ctx, void* dst_h, const void* src_d, size_t bytes); /* async */
+int nxfx_memcpy_d2d(nxfx_ctx* ctx, void* dst_d, const void* src_d, size_t bytes); /* async */
+int nxfx_memset(nxfx_ctx* ctx, void* dst_d, int byte, size_t bytes);              /* async */
+/* CUDA-event timer on the ctx stream (bench.py) */
+int nxfx_timer_start(nxfx_ctx* ctx);
+int nxfx_timer_stop(nxfx_ctx* ctx, double* elapsed_ms); /* synchronises */
+
+/* ---- (1) graph -> mesh -------------------------------------------------------------------- *
+ * Replaces the mesh-array construction and dolfinx.mesh.create_mesh: mesh.py:270-324, 341-348.
+ * Inputs are the host-side graph tables built by NetworkMesh (mesh.py:175-225):
+ *   node_pos_h [n_nodes*gdim]  node coordinates in graph.nodes() order
+ *   edge_u_h/edge_v_h [n_edges] endpoints in graph.edges() order (cells run u -> v)
+ *   edge_slot_h [n_edges]       flux slot of the edge: its N+1 flux dofs are rows
+ *                               slot*(N+1) .. slot*(N+1)+N  (slot = colour-block offset + rank)
+ *   node_lm_h [n_nodes]         multiplier index of the node (position in bifurcation_values)
+ *                               or -1 for non-bifurcation nodes
+ *   bif_ptr_h [n_bif+1], bif_inc_h [I]  incidences of each bifurcation, sorted by flux slot:
+ *                               entry = 2*edge + 1 for an in-edge (edge ends at the node),
+ *                               2*edge for an out-edge.
+ * Builds on the device: vertex coordinates x[n_vertices][3] (graph nodes first, then the N-1
+ * interior points of every edge, start*(1-w)+end*w, bit-identical to the reference formula).     */
+int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gdim,
+                     int32_t cells_per_edge, const double* node_pos_h, const int32_t* edge_u_h,
+                     const int32_t* edge_v_h, const int32_t* edge_slot_h, const int32_t* node_lm_h,
+                     int32_t n_bif, const int32_t* bif_ptr_h, const int32_t* bif_inc_h);
+/* re-upload node positions (same topology) and regenerate the vertex coordinates */
+int nxfx_update_node_positions(nxfx_ctx* ctx, const double* node_pos_h);
+int nxfx_get_sizes(const nxfx_ctx* ctx, int64_t* n_vertices, int64_t* n_cells, int64_t* n_dofs,
+                   int64_t* nnz);
+int nxfx_mesh_geometry_device(nxfx_ctx* ctx, const double** x_d); /* [n_vertices][3] */
+
+/* ---- (2) symbolic phase ------------------------------------------------------------------- *
+ * Replaces dolfinx.fem.petsc.create_matrix (sparsity pattern + preallocation): solver.py:43,
+ * assembly.py:354.  Builds the CSR pattern (rowptr, sorted colidx) on the device, including the
+ * explicit zeros DOLFINx stores in the multiplier blocks.                                         */
+int nxfx_symbolic(nxfx_ctx* ctx);
+int nxfx_csr_device(nxfx_ctx* ctx, const int32_t** rowptr_d, const int32_t** colidx_d,
+                    double** values_d);
+
+/* ---- (3) numeric assembly ----------------------------------------------------------------- *
+ * Replaces fem.petsc.assemble_matrix + A.assemble() + assemble_vector + ghost update:
+ * assembly.py:352-367 (forms: assembly.py:253-277).
+ *   pbc_vertex_d [n_vertices]   p_bc interpolated into P1 on the parent mesh (assembly.py:225-234)
+ *   R_cell_d / f_cell_d [n_cells] per-cell coefficients, or NULL to use R_const / f_const
+ *                               (defaults R=1, f=0: assembly.py:201-205)
+ *   lhs / rhs                   assemble_lhs / assemble_rhs flags (assembly.py:333-334)
+ *   accumulate                  0: overwrite (the matrix/vector was zeroed: solver.py:97-100);
+ *                               1: add to the existing entries (PETSc ADD_VALUES semantics)
+ *   b_d [n_dofs]                right-hand side (written when rhs != 0)
+ * Matrix values go to the ctx-owned CSR value array (nxfx_csr_device).                            */
+int nxfx_assemble(nxfx_ctx* ctx, const double* pbc_vertex_d, const double* R_cell_d, double R_const,
+                  const double* f_cell_d, double f_const, int lhs, int rhs, int accumulate,
+                  double* b_d);
+
+/* ---- (4) solve ---------------------------------------------------------------------------- *
+ * Replaces KSP/PC/MUMPS: solver.py:41,51,58-73,127.                                              */
+typedef enum { NXFX_KSP_PREONLY = 0, NXFX_KSP_FGMRES = 1 } nxfx_ksp_type;
+typedef enum {
+  NXFX_PC_NETWORK_SCHUR = 0, /* exact Schur complement on the multipliers (tree elimination) */
+  NXFX_PC_NONE = 1,
+  NXFX_PC_JACOBI_FLUX = 2    /* diag(M) on fluxes, identity elsewhere */
+} nxfx_pc_type;
+
+typedef struct {
+  int32_t ksp_type;     /* nxfx_ksp_type */
+  int32_t pc_type;      /* nxfx_pc_type */
+  double rtol;          /* relative residual tolerance ||b-Ax|| / ||b|| */
+  double atol;
+  int32_t max_it;
+  int32_t restart;      /* FGMRES restart length */
+  int32_t refine_steps; /* PREONLY: iterative-refinement steps after the first apply */
+  int32_t error_if_not_converged;
+} nxfx_solve_opts;
+
+#define NXFX_HISTORY_LEN 128
+typedef struct {
+  int32_t iterations;
+  int32_t converged;
+  double rhs_norm;
+  double residual_norm;               /* final true residual ||b - A x||_2 */
+  int32_t history_len;
+  double history[NXFX_HISTORY_LEN];   /* residual norms (ksp_monitor) */
+} nxfx_solve_info;
+
+/* Elimination schedule of the bifurcation tree, built on the host by the Solver from the graph:
+ *   t_of_bif [n_bif]      position of each multiplier in schedule order
+ *   t_parent [n_bif]      parent (schedule index) or -1
+ *   t_pedge  [n_bif]      graph edge joining the node to its parent or -1
+ *   t_cptr [n_bif+1], t_cidx [..]  children lists (schedule indices)
+ *   n_chunks, chunk_lptr [n_chunks+1]  chunks = subtrees solved by one thread block; the LAST
+ *                         chunk is the top of the forest.  Levels of chunk c are
+ *                         lvl_ptr[chunk_lptr[c] .. chunk_lptr[c+1]] (ranges of schedule indices,
+ *                         shallowest level first).
+ *   n_chords, chord_edge  graph edges between bifurcations that are not in the spanning forest
+ *                         (cyclic graphs; their conductance stays on the diagonals only).          */
+int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif_h, const int32_t* t_parent_h,
+                           const int32_t* t_pedge_h, const int32_t* t_cptr_h,
+                           const int32_t* t_cidx_h, int32_t n_chunks, const int32_t* chunk_lptr_h,
+                           int32_t n_lvl_ptr, const int32_t* lvl_ptr_h, int32_t n_chords,
+                           const int32_t* chord_edge_h);
+int nxfx_pc_setup(nxfx_ctx* ctx);                                    /* numeric factorisation */
+int nxfx_pc_apply(nxfx_ctx* ctx, const double* r_d, double* z_d);    /* z = P^{-1} r */
+int nxfx_spmv(nxfx_ctx* ctx, const double* x_d, double* y_d);        /* y = A x */
+int nxfx_residual(nxfx_ctx* ctx, const double* b_d, const double* x_d, double* r_d,
+                  double* norm2_h);  /* r = b - A x; *norm2_h = ||r||_2^2 (synchronises) */
+int nxfx_solve(nxfx_ctx* ctx, const double* b_d, double* x_d, const nxfx_solve_opts* opts,
+               nxfx_solve_info* info); /* synchronises before returning */
+
+/* ---- (5) end-to-end host-buffer call (bench.py "e2e") -------------------------------------- *
+ * One assemble+solve step with HOST inputs and outputs: uploads node positions and p_bc vertex
+ * values, regenerates the vertices, assembles, solves, downloads x.  All host pointers should be
+ * pinned (nxfx_host_alloc) for full PCIe bandwidth.                                               */
+int nxfx_assemble_solve_host(nxfx_ctx* ctx, const double* node_pos_h, const double* pbc_vertex_h,
+                             double R_const, double f_const, const nxfx_solve_opts* opts,
+                             double* x_h, nxfx_solve_info* info);
+
+/* ---- post-processing ----------------------------------------------------------------------- *
+ * Replaces Function.interpolate into the DG space in extract_global_flux: post_processing.py:36-51.
+ * out_d [2*n_cells]: DG1 dofs (cell-wise [q(first vertex), q(second vertex)]).                       */
+int nxfx_global_flux(nxfx_ctx* ctx, const double* x_d, double* out_d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NXFX_B200_H */

@@ -1,0 +1,116 @@
+// Context, error handling and device-buffer helpers of libnxfx_b200 (sm_100a, FP64).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nxfx_b200.h"
+
+namespace nxfx {
+
+constexpr int kTileRows = 256;     // rows per thread block in the row-tiled kernels
+constexpr int kTileCap = 2048;     // CSR entries staged in shared memory per tile
+constexpr int kThreads = 256;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+struct TreeSchedule {
+  bool set = false;
+  int n_chunks = 0, n_lvl_ptr = 0, n_chords = 0;
+  DevBuf<int32_t> t_of_bif, t_parent, t_pedge, t_cptr, t_cidx, chunk_lptr, lvl_ptr, chord_edge;
+  std::vector<int32_t> chunk_lptr_h, lvl_ptr_h;
+  // numeric
+  DevBuf<double> diag0, d, gd, r, lam;  // schedule order
+};
+
+}  // namespace nxfx
+
+struct nxfx_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 148;
+
+  // network
+  bool has_network = false, has_pattern = false, assembled = false, pc_ready = false;
+  int32_t n_nodes = 0, E = 0, gdim = 0, N = 0, n_bif = 0, n_inc = 0;
+  int64_t nv = 0, nc = 0, nq = 0, poff = 0, loff = 0, ndofs = 0, nnz = 0;
+  nxfx::DevBuf<double> x;          // [nv][3] vertex coordinates (graph nodes first)
+  nxfx::DevBuf<double> pos_stage;  // [n_nodes*gdim] upload staging
+  nxfx::DevBuf<int4> slot_uvl;     // [E] {u, v, lm(u), lm(v)} in slot order
+  nxfx::DevBuf<int32_t> slot_edge, edge_slot, edge_u, edge_v, bif_ptr, bif_inc;
+  // pattern + values
+  nxfx::DevBuf<int32_t> rowptr, colidx;
+  nxfx::DevBuf<double> vals;
+  nxfx::DevBuf<double> cell_rh;  // [nc] R*h per cell, written by the assembly kernel
+  // solver workspace
+  nxfx::TreeSchedule tree;
+  nxfx::DevBuf<double> edge_g, edge_c, edge_fn;  // [E] conductance, condensed rhs, F_N
+  nxfx::DevBuf<double> work;                     // krylov vectors
+  nxfx::DevBuf<double> scal;                     // device scalars / partials
+  nxfx::DevBuf<unsigned int> ticket;
+  double* scal_h = nullptr;  // pinned mirror
+  // e2e staging
+  nxfx::DevBuf<double> e2e_pbc, e2e_b, e2e_x;
+};
+
+namespace nxfx {
+
+inline int fail(nxfx_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define NXFX_CUDA(ctx, call)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return nxfx::fail(ctx, NXFX_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,     \
+                        cudaGetErrorString(_e));                                              \
+  } while (0)
+
+#define NXFX_REQUIRE(ctx, cond, msg)                                                          \
+  do {                                                                                        \
+    if (!(cond)) return nxfx::fail(ctx, NXFX_ERR_INVALID, "%s: %s", __func__, msg);           \
+  } while (0)
+
+// launch + count + check
+#define NXFX_LAUNCH(ctx, kernel, grid, block, smem, ...)                                      \
+  do {                                                                                        \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                          \
+    (ctx)->launches++;                                                                        \
+    NXFX_CUDA(ctx, cudaGetLastError());                                                       \
+  } while (0)
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace nxfx

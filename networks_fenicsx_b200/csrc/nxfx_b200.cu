@@ -1,0 +1,708 @@
+// libnxfx_b200: C ABI of the B200-native hydraulic-network assemble+solve path.
+// See include/nxfx_b200.h for the contract and the reference call sites each entry replaces.
+
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+
+#include "assemble.cuh"
+#include "ctx.cuh"
+#include "precond.cuh"
+#include "spmv.cuh"
+
+using namespace nxfx;
+
+namespace {
+
+constexpr int kScalPartials = 8 * kMaxPartials;  // partial sums for up to 8 fused dots
+constexpr int kScalSlots = 1024;                 // device scalars after the partials
+
+Net make_net(const nxfx_ctx* c) {
+  Net g;
+  g.n_nodes = c->n_nodes;
+  g.E = c->E;
+  g.N = c->N;
+  g.n_bif = c->n_bif;
+  g.nq = (int32_t)c->nq;
+  g.poff = (int32_t)c->poff;
+  g.loff = (int32_t)c->loff;
+  g.ndofs = (int32_t)c->ndofs;
+  g.slot_uvl = c->slot_uvl.p;
+  g.slot_edge = c->slot_edge.p;
+  g.edge_slot = c->edge_slot.p;
+  g.bif_ptr = c->bif_ptr.p;
+  g.bif_inc = c->bif_inc.p;
+  g.x = c->x.p;
+  return g;
+}
+
+TreeDev make_tree(nxfx_ctx* c) {
+  TreeDev t;
+  auto& s = c->tree;
+  t.t_of_bif = s.t_of_bif.p;
+  t.t_parent = s.t_parent.p;
+  t.t_pedge = s.t_pedge.p;
+  t.t_cptr = s.t_cptr.p;
+  t.t_cidx = s.t_cidx.p;
+  t.chunk_lptr = s.chunk_lptr.p;
+  t.lvl_ptr = s.lvl_ptr.p;
+  t.diag0 = s.diag0.p;
+  t.d = s.d.p;
+  t.gd = s.gd.p;
+  t.r = s.r.p;
+  t.lam = s.lam.p;
+  return t;
+}
+
+int vec_grid(const nxfx_ctx* c, int64_t n) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, kThreads), (int64_t)c->sm_count * 8));
+}
+
+template <typename T>
+int upload(nxfx_ctx* ctx, DevBuf<T>& buf, const T* src, size_t n) {
+  NXFX_CUDA(ctx, buf.alloc(n));
+  if (n) NXFX_CUDA(ctx, cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return NXFX_OK;
+}
+
+int ensure_scal(nxfx_ctx* ctx) {
+  if (ctx->scal.p) return NXFX_OK;
+  NXFX_CUDA(ctx, ctx->scal.alloc(kScalPartials + kScalSlots));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->scal.p, 0, (kScalPartials + kScalSlots) * sizeof(double), ctx->stream));
+  NXFX_CUDA(ctx, ctx->ticket.alloc(1));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned int), ctx->stream));
+  NXFX_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->scal_h), kScalSlots * sizeof(double), cudaHostAllocDefault));
+  return NXFX_OK;
+}
+
+double* slot(nxfx_ctx* ctx, int i) { return ctx->scal.p + kScalPartials + i; }
+
+int build_vertices(nxfx_ctx* ctx) {
+  const int n3 = ctx->n_nodes * 3;
+  NXFX_LAUNCH(ctx, pad_nodes_kernel, (int)cdiv(n3, kThreads), kThreads, 0, ctx->n_nodes, ctx->gdim,
+              ctx->pos_stage.p, ctx->x.p);
+  if (ctx->N > 1) {
+    const int64_t total = (int64_t)ctx->E * (ctx->N - 1) * 3;
+    NXFX_LAUNCH(ctx, interior_vertices_kernel, vec_grid(ctx, total), kThreads, 0, ctx->n_nodes,
+                ctx->E, ctx->N, ctx->edge_u.p, ctx->edge_v.p, ctx->x.p);
+  }
+  return NXFX_OK;
+}
+
+// ---- solver building blocks ------------------------------------------------------------------
+int do_spmv(nxfx_ctx* ctx, const double* x, double* y) {
+  const int ntiles = (int)cdiv(ctx->ndofs, kTileRows);
+  NXFX_LAUNCH(ctx, spmv_kernel<0>, ntiles, kTileRows, 0, (int)ctx->ndofs, ntiles, ctx->rowptr.p,
+              ctx->colidx.p, ctx->vals.p, x, y, nullptr, nullptr, nullptr, nullptr);
+  return NXFX_OK;
+}
+
+int do_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, double* norm2_d) {
+  const int ntiles = (int)cdiv(ctx->ndofs, kTileRows);
+  const int grid = std::min(ntiles, kMaxPartials);
+  NXFX_LAUNCH(ctx, spmv_kernel<1>, grid, kTileRows, 0, (int)ctx->ndofs, ntiles, ctx->rowptr.p,
+              ctx->colidx.p, ctx->vals.p, x, r, b, ctx->scal.p, ctx->ticket.p, norm2_d);
+  return NXFX_OK;
+}
+
+template <int K>
+int launch_multi_dot(nxfx_ctx* ctx, int n, const double* A, size_t stride, const double* w, double* out) {
+  NXFX_LAUNCH(ctx, multi_dot_kernel<K>, vec_grid(ctx, n), kThreads, 0, n, A, stride, w, ctx->scal.p,
+              ctx->ticket.p, out);
+  return NXFX_OK;
+}
+
+int do_multi_dot(nxfx_ctx* ctx, int n, int k, const double* A, size_t stride, const double* w, double* out) {
+  int j = 0;
+  while (j < k) {
+    const int m = std::min(8, k - j);
+    const double* Aj = A + (size_t)j * stride;
+    int rc = NXFX_OK;
+    switch (m) {
+      case 8: rc = launch_multi_dot<8>(ctx, n, Aj, stride, w, out + j); break;
+      case 7: rc = launch_multi_dot<7>(ctx, n, Aj, stride, w, out + j); break;
+      case 6: rc = launch_multi_dot<6>(ctx, n, Aj, stride, w, out + j); break;
+      case 5: rc = launch_multi_dot<5>(ctx, n, Aj, stride, w, out + j); break;
+      case 4: rc = launch_multi_dot<4>(ctx, n, Aj, stride, w, out + j); break;
+      case 3: rc = launch_multi_dot<3>(ctx, n, Aj, stride, w, out + j); break;
+      case 2: rc = launch_multi_dot<2>(ctx, n, Aj, stride, w, out + j); break;
+      default: rc = launch_multi_dot<1>(ctx, n, Aj, stride, w, out + j); break;
+    }
+    if (rc) return rc;
+    j += m;
+  }
+  return NXFX_OK;
+}
+
+template <int K>
+int launch_multi_axpy(nxfx_ctx* ctx, int n, const double* A, size_t stride, const double* h, double sign, double* w) {
+  NXFX_LAUNCH(ctx, multi_axpy_kernel<K>, vec_grid(ctx, n), kThreads, 0, n, A, stride, h, sign, w);
+  return NXFX_OK;
+}
+
+int do_multi_axpy(nxfx_ctx* ctx, int n, int k, const double* A, size_t stride, const double* h, double sign, double* w) {
+  int j = 0;
+  while (j < k) {
+    const int m = std::min(8, k - j);
+    const double* Aj = A + (size_t)j * stride;
+    int rc = NXFX_OK;
+    switch (m) {
+      case 8: rc = launch_multi_axpy<8>(ctx, n, Aj, stride, h + j, sign, w); break;
+      case 7: rc = launch_multi_axpy<7>(ctx, n, Aj, stride, h + j, sign, w); break;
+      case 6: rc = launch_multi_axpy<6>(ctx, n, Aj, stride, h + j, sign, w); break;
+      case 5: rc = launch_multi_axpy<5>(ctx, n, Aj, stride, h + j, sign, w); break;
+      case 4: rc = launch_multi_axpy<4>(ctx, n, Aj, stride, h + j, sign, w); break;
+      case 3: rc = launch_multi_axpy<3>(ctx, n, Aj, stride, h + j, sign, w); break;
+      case 2: rc = launch_multi_axpy<2>(ctx, n, Aj, stride, h + j, sign, w); break;
+      default: rc = launch_multi_axpy<1>(ctx, n, Aj, stride, h + j, sign, w); break;
+    }
+    if (rc) return rc;
+    j += m;
+  }
+  return NXFX_OK;
+}
+
+int tree_pass(nxfx_ctx* ctx, bool factor) {
+  auto& s = ctx->tree;
+  TreeDev t = make_tree(ctx);
+  const int nb = s.n_chunks - 1;  // bottom chunks; the last chunk is the top of the forest
+  if (factor) {
+    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<0>, nb, 1024, 0, t, ctx->edge_g.p, 0);
+    NXFX_LAUNCH(ctx, tree_sweep_kernel<0>, 1, 1024, 0, t, ctx->edge_g.p, nb);
+  } else {
+    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<1>, nb, 1024, 0, t, ctx->edge_g.p, 0);
+    NXFX_LAUNCH(ctx, tree_sweep_kernel<3>, 1, 1024, 0, t, ctx->edge_g.p, nb);
+    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<2>, nb, 1024, 0, t, ctx->edge_g.p, 0);
+  }
+  return NXFX_OK;
+}
+
+int do_pc_setup(nxfx_ctx* ctx) {
+  NXFX_REQUIRE(ctx, ctx->assembled, "assemble the matrix before pc_setup");
+  NXFX_REQUIRE(ctx, ctx->tree.set, "nxfx_set_tree_schedule has not been called");
+  NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N,
+              ctx->cell_rh.p, ctx->edge_g.p);
+  if (ctx->n_bif > 0) {
+    NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx),
+                make_tree(ctx), ctx->edge_g.p);
+    int rc = tree_pass(ctx, true);
+    if (rc) return rc;
+  }
+  ctx->pc_ready = true;
+  return NXFX_OK;
+}
+
+int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z) {
+  const int n = (int)ctx->ndofs;
+  if (pc_type == NXFX_PC_NONE) {
+    NXFX_CUDA(ctx, cudaMemcpyAsync(z, r, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return NXFX_OK;
+  }
+  if (pc_type == NXFX_PC_JACOBI_FLUX) {
+    NXFX_LAUNCH(ctx, jacobi_flux_kernel, (int)cdiv(n, kThreads), kThreads, 0, n, (int)ctx->nq,
+                ctx->rowptr.p, ctx->colidx.p, ctx->vals.p, r, z);
+    return NXFX_OK;
+  }
+  NXFX_REQUIRE(ctx, ctx->pc_ready, "pc_setup has not been run");
+  Net g = make_net(ctx);
+  TreeDev t = make_tree(ctx);
+  NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p,
+              r, ctx->edge_c.p, ctx->edge_fn.p);
+  if (ctx->n_bif > 0) {
+    NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r,
+                ctx->edge_g.p, ctx->edge_c.p, ctx->edge_fn.p);
+    int rc = tree_pass(ctx, false);
+    if (rc) return rc;
+  }
+  NXFX_LAUNCH(ctx, edge_backsub_kernel, (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads), kThreads, 0,
+              g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+  return NXFX_OK;
+}
+
+int ensure_work(nxfx_ctx* ctx, size_t nvec) {
+  const size_t need = nvec * (size_t)ctx->ndofs;
+  if (ctx->work.n >= need) return NXFX_OK;
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  NXFX_CUDA(ctx, ctx->work.alloc(need));
+  return NXFX_OK;
+}
+
+void push_history(nxfx_solve_info* info, double v) {
+  if (info->history_len < NXFX_HISTORY_LEN) info->history[info->history_len++] = v;
+}
+
+// x = P^{-1} b followed by `refine_steps` steps of iterative refinement; one sync at the end.
+int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts* o, nxfx_solve_info* info) {
+  const int n = (int)ctx->ndofs;
+  int rc = ensure_work(ctx, 2);
+  if (rc) return rc;
+  double* r = ctx->work.p;
+  double* z = ctx->work.p + n;
+  const int steps = std::max(0, std::min(o->refine_steps, 32));
+  if ((rc = do_multi_dot(ctx, n, 1, b, 0, b, slot(ctx, 0)))) return rc;
+  if ((rc = do_pc_apply(ctx, o->pc_type, b, x))) return rc;
+  for (int s = 0; s < steps; ++s) {
+    if ((rc = do_residual(ctx, b, x, r, slot(ctx, 1 + s)))) return rc;
+    if ((rc = do_pc_apply(ctx, o->pc_type, r, z))) return rc;
+    NXFX_LAUNCH(ctx, add_kernel, vec_grid(ctx, n), kThreads, 0, n, z, x);
+  }
+  if ((rc = do_residual(ctx, b, x, r, slot(ctx, 1 + steps)))) return rc;
+  NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, slot(ctx, 0), (steps + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  info->rhs_norm = std::sqrt(ctx->scal_h[0]);
+  for (int s = 0; s <= steps; ++s) push_history(info, std::sqrt(ctx->scal_h[1 + s]));
+  info->residual_norm = std::sqrt(ctx->scal_h[1 + steps]);
+  info->iterations = 1 + steps;
+  const double tol = std::max(o->rtol * info->rhs_norm, o->atol);
+  info->converged = std::isfinite(info->residual_norm) && info->residual_norm <= tol;
+  return NXFX_OK;
+}
+
+// Right-preconditioned flexible GMRES(m), classical Gram-Schmidt with one re-orthogonalisation
+// (two fused multi-dots per iteration), Givens rotations on the host: one readback per iteration.
+int solve_fgmres(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts* o, nxfx_solve_info* info) {
+  const int n = (int)ctx->ndofs;
+  const int m = std::max(1, std::min(o->restart > 0 ? o->restart : 30, 200));
+  NXFX_REQUIRE(ctx, 2 * (m + 2) + 8 < kScalSlots, "restart too large");
+  int rc = ensure_work(ctx, (size_t)(2 * m + 3));
+  if (rc) return rc;
+  double* V = ctx->work.p;                       // m+1 vectors
+  double* Z = V + (size_t)(m + 1) * n;           // m vectors
+  double* w = Z + (size_t)m * n;                 // 1
+  double* r = w + n;                             // 1
+  double* hcol = slot(ctx, 8);                   // h[0..k], then ||w||^2
+  double* hcol2 = slot(ctx, 8 + m + 2);          // second Gram-Schmidt pass
+  double* ycoef = slot(ctx, 8 + 2 * (m + 2));    // solution of the small system (<= m)
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gvec(m + 1), y(m);
+
+  NXFX_CUDA(ctx, cudaMemsetAsync(x, 0, n * sizeof(double), ctx->stream));
+  if ((rc = do_multi_dot(ctx, n, 1, b, 0, b, slot(ctx, 0)))) return rc;
+  int its = 0;
+  const int max_it = o->max_it > 0 ? o->max_it : 10000;
+  double tol = 0.0;
+  while (true) {
+    if ((rc = do_residual(ctx, b, x, r, slot(ctx, 1)))) return rc;
+    NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, slot(ctx, 0), 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    info->rhs_norm = std::sqrt(ctx->scal_h[0]);
+    const double beta = std::sqrt(ctx->scal_h[1]);
+    tol = std::max(o->rtol * info->rhs_norm, o->atol);
+    info->residual_norm = beta;
+    push_history(info, beta);
+    if (!(beta > tol) || its >= max_it || !std::isfinite(beta)) break;
+    NXFX_LAUNCH(ctx, scale_by_inv_norm_kernel, vec_grid(ctx, n), kThreads, 0, n, r, slot(ctx, 1), V);
+    std::fill(gvec.begin(), gvec.end(), 0.0);
+    gvec[0] = beta;
+    int k = 0;
+    for (; k < m && its < max_it; ++k, ++its) {
+      double* vk = V + (size_t)k * n;
+      double* zk = Z + (size_t)k * n;
+      if ((rc = do_pc_apply(ctx, o->pc_type, vk, zk))) return rc;
+      if ((rc = do_spmv(ctx, zk, w))) return rc;
+      if ((rc = do_multi_dot(ctx, n, k + 1, V, n, w, hcol))) return rc;
+      if ((rc = do_multi_axpy(ctx, n, k + 1, V, n, hcol, -1.0, w))) return rc;
+      if ((rc = do_multi_dot(ctx, n, k + 1, V, n, w, hcol2))) return rc;
+      if ((rc = do_multi_axpy(ctx, n, k + 1, V, n, hcol2, -1.0, w))) return rc;
+      if ((rc = do_multi_dot(ctx, n, 1, w, 0, w, hcol + k + 1))) return rc;
+      NXFX_LAUNCH(ctx, scale_by_inv_norm_kernel, vec_grid(ctx, n), kThreads, 0, n, w, hcol + k + 1,
+                  V + (size_t)(k + 1) * n);
+      NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, hcol, (2 * (m + 2)) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      double* Hk = &H[(size_t)k * (m + 1)];
+      for (int i = 0; i <= k; ++i) Hk[i] = ctx->scal_h[i] + ctx->scal_h[m + 2 + i];
+      Hk[k + 1] = std::sqrt(ctx->scal_h[k + 1]);
+      for (int i = 0; i < k; ++i) {
+        const double t = cs[i] * Hk[i] + sn[i] * Hk[i + 1];
+        Hk[i + 1] = -sn[i] * Hk[i] + cs[i] * Hk[i + 1];
+        Hk[i] = t;
+      }
+      const double den = std::hypot(Hk[k], Hk[k + 1]);
+      cs[k] = den > 0 ? Hk[k] / den : 1.0;
+      sn[k] = den > 0 ? Hk[k + 1] / den : 0.0;
+      Hk[k] = den;
+      gvec[k + 1] = -sn[k] * gvec[k];
+      gvec[k] = cs[k] * gvec[k];
+      const double est = std::fabs(gvec[k + 1]);
+      push_history(info, est);
+      if (est <= tol || !std::isfinite(est)) { ++k; ++its; break; }
+    }
+    for (int i = k - 1; i >= 0; --i) {
+      double s = gvec[i];
+      for (int j = i + 1; j < k; ++j) s -= H[(size_t)j * (m + 1) + i] * y[j];
+      y[i] = s / H[(size_t)i * (m + 1) + i];
+    }
+    if (k > 0) {
+      std::copy(y.begin(), y.begin() + k, ctx->scal_h + 512);
+      NXFX_CUDA(ctx, cudaMemcpyAsync(ycoef, ctx->scal_h + 512, k * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      if ((rc = do_multi_axpy(ctx, n, k, Z, n, ycoef, 1.0, x))) return rc;
+    }
+  }
+  info->iterations = its;
+  info->converged = std::isfinite(info->residual_norm) && info->residual_norm <= tol;
+  return NXFX_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int nxfx_abi_version(void) { return NXFX_ABI_VERSION; }
+
+int nxfx_create(nxfx_ctx** out, int device) {
+  if (!out) return NXFX_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || device < 0 || device >= count) return NXFX_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return NXFX_ERR_CUDA;
+  auto* ctx = new nxfx_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  *out = ctx;
+  return NXFX_OK;
+}
+
+int nxfx_destroy(nxfx_ctx* ctx) {
+  if (!ctx) return NXFX_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->scal_h) cudaFreeHost(ctx->scal_h);
+  delete ctx;
+  return NXFX_OK;
+}
+
+const char* nxfx_last_error(const nxfx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int nxfx_set_stream(nxfx_ctx* ctx, void* s) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  ctx->stream = reinterpret_cast<cudaStream_t>(s);
+  return NXFX_OK;
+}
+
+int nxfx_sync(nxfx_ctx* ctx) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NXFX_OK;
+}
+
+int64_t nxfx_launch_count(const nxfx_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int nxfx_malloc(nxfx_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return NXFX_ERR_INVALID;
+  NXFX_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 8));
+  return NXFX_OK;
+}
+int nxfx_free(nxfx_ctx* ctx, void* p) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_CUDA(ctx, cudaFree(p));
+  return NXFX_OK;
+}
+int nxfx_host_alloc(nxfx_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return NXFX_ERR_INVALID;
+  NXFX_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 8, cudaHostAllocDefault));
+  return NXFX_OK;
+}
+int nxfx_host_free(nxfx_ctx* ctx, void* p) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_CUDA(ctx, cudaFreeHost(p));
+  return NXFX_OK;
+}
+int nxfx_memcpy_h2d(nxfx_ctx* ctx, void* d, const void* s, size_t bytes) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_CUDA(ctx, cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return NXFX_OK;
+}
+int nxfx_memcpy_d2h(nxfx_ctx* ctx, void* d, const void* s, size_t bytes) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_CUDA(ctx, cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return NXFX_OK;
+}
+int nxfx_memcpy_d2d(nxfx_ctx* ctx, void* d, const void* s, size_t bytes) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_CUDA(ctx, cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return NXFX_OK;
+}
+int nxfx_memset(nxfx_ctx* ctx, void* d, int byte, size_t bytes) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_CUDA(ctx, cudaMemsetAsync(d, byte, bytes, ctx->stream));
+  return NXFX_OK;
+}
+int nxfx_timer_start(nxfx_ctx* ctx) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return NXFX_OK;
+}
+int nxfx_timer_stop(nxfx_ctx* ctx, double* ms) {
+  if (!ctx || !ms) return NXFX_ERR_INVALID;
+  NXFX_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  NXFX_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  float f = 0.f;
+  NXFX_CUDA(ctx, cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+  *ms = f;
+  return NXFX_OK;
+}
+
+// ---- (1) graph -> mesh -------------------------------------------------------------------------
+int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gdim, int32_t N,
+                     const double* node_pos, const int32_t* edge_u, const int32_t* edge_v,
+                     const int32_t* edge_slot, const int32_t* node_lm, int32_t n_bif,
+                     const int32_t* bif_ptr, const int32_t* bif_inc) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, n_nodes > 0 && n_edges > 0 && N >= 1 && gdim >= 1 && gdim <= 3, "bad sizes");
+  NXFX_REQUIRE(ctx, node_pos && edge_u && edge_v && edge_slot && node_lm && bif_ptr, "null input");
+  NXFX_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t E = n_edges;
+  const int64_t nq = E * (N + 1), nc = E * N, ndofs = nq + nc + n_bif;
+  const int64_t nv = (int64_t)n_nodes + E * (N - 1);
+  NXFX_REQUIRE(ctx, ndofs < (int64_t)2147483000 && nv * 3 < (int64_t)2147483000, "network too large for int32 indexing");
+  const int32_t n_inc = bif_ptr[n_bif];
+  NXFX_REQUIRE(ctx, n_inc == 0 || bif_inc, "null incidence list");
+  // host-side validation + slot tables
+  std::vector<int4> uvl((size_t)E);
+  std::vector<int32_t> slot_edge((size_t)E, -1);
+  for (int64_t e = 0; e < E; ++e) {
+    const int32_t u = edge_u[e], v = edge_v[e], s = edge_slot[e];
+    if (u < 0 || u >= n_nodes || v < 0 || v >= n_nodes || u == v)
+      return fail(ctx, NXFX_ERR_INVALID, "edge %lld has invalid endpoints (%d, %d)", (long long)e, u, v);
+    if (s < 0 || s >= E || slot_edge[s] != -1)
+      return fail(ctx, NXFX_ERR_INVALID, "edge_slot is not a permutation (edge %lld -> %d)", (long long)e, s);
+    if (node_lm[u] >= n_bif || node_lm[v] >= n_bif)
+      return fail(ctx, NXFX_ERR_INVALID, "node_lm out of range at edge %lld", (long long)e);
+    slot_edge[s] = (int32_t)e;
+    uvl[s] = make_int4(u, v, node_lm[u], node_lm[v]);
+  }
+  for (int32_t k = 0; k < n_inc; ++k)
+    if ((bif_inc[k] >> 1) < 0 || (bif_inc[k] >> 1) >= E)
+      return fail(ctx, NXFX_ERR_INVALID, "bif_inc[%d] out of range", k);
+  ctx->has_network = ctx->has_pattern = ctx->assembled = ctx->pc_ready = false;
+  ctx->tree.set = false;
+  ctx->n_nodes = n_nodes; ctx->E = n_edges; ctx->gdim = gdim; ctx->N = N; ctx->n_bif = n_bif;
+  ctx->n_inc = n_inc; ctx->nv = nv; ctx->nc = nc; ctx->nq = nq; ctx->poff = nq; ctx->loff = nq + nc;
+  ctx->ndofs = ndofs; ctx->nnz = 0;
+  int rc;
+  if ((rc = upload(ctx, ctx->pos_stage, node_pos, (size_t)n_nodes * gdim))) return rc;
+  if ((rc = upload(ctx, ctx->edge_u, edge_u, (size_t)E))) return rc;
+  if ((rc = upload(ctx, ctx->edge_v, edge_v, (size_t)E))) return rc;
+  if ((rc = upload(ctx, ctx->edge_slot, edge_slot, (size_t)E))) return rc;
+  if ((rc = upload(ctx, ctx->slot_edge, slot_edge.data(), (size_t)E))) return rc;
+  if ((rc = upload(ctx, ctx->slot_uvl, uvl.data(), (size_t)E))) return rc;
+  if ((rc = upload(ctx, ctx->bif_ptr, bif_ptr, (size_t)n_bif + 1))) return rc;
+  if ((rc = upload(ctx, ctx->bif_inc, bif_inc, (size_t)n_inc))) return rc;
+  NXFX_CUDA(ctx, ctx->x.alloc((size_t)nv * 3));
+  NXFX_CUDA(ctx, ctx->cell_rh.alloc((size_t)nc));
+  NXFX_CUDA(ctx, ctx->edge_g.alloc((size_t)E));
+  NXFX_CUDA(ctx, ctx->edge_c.alloc((size_t)E));
+  NXFX_CUDA(ctx, ctx->edge_fn.alloc((size_t)E));
+  if ((rc = ensure_scal(ctx))) return rc;
+  if ((rc = build_vertices(ctx))) return rc;
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+  ctx->has_network = true;
+  return NXFX_OK;
+}
+
+int nxfx_update_node_positions(nxfx_ctx* ctx, const double* node_pos) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_network && node_pos, "no network / null input");
+  NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->pos_stage.p, node_pos, (size_t)ctx->n_nodes * ctx->gdim * sizeof(double),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+  return build_vertices(ctx);
+}
+
+int nxfx_get_sizes(const nxfx_ctx* ctx, int64_t* nv, int64_t* nc, int64_t* ndofs, int64_t* nnz) {
+  if (!ctx || !ctx->has_network) return NXFX_ERR_INVALID;
+  if (nv) *nv = ctx->nv;
+  if (nc) *nc = ctx->nc;
+  if (ndofs) *ndofs = ctx->ndofs;
+  if (nnz) *nnz = ctx->nnz;
+  return NXFX_OK;
+}
+
+int nxfx_mesh_geometry_device(nxfx_ctx* ctx, const double** x) {
+  if (!ctx || !x) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_network, "no network");
+  *x = ctx->x.p;
+  return NXFX_OK;
+}
+
+// ---- (2) symbolic --------------------------------------------------------------------------------
+int nxfx_symbolic(nxfx_ctx* ctx) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_network, "no network");
+  const int n = (int)ctx->ndofs;
+  Net g = make_net(ctx);
+  DevBuf<int32_t> len;
+  NXFX_CUDA(ctx, len.alloc((size_t)n + 1));
+  NXFX_CUDA(ctx, ctx->rowptr.alloc((size_t)n + 1));
+  NXFX_LAUNCH(ctx, row_len_kernel, (int)cdiv(n + 1, kThreads), kThreads, 0, g, len.p);
+  size_t tmp_bytes = 0;
+  NXFX_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len.p, ctx->rowptr.p, n + 1, ctx->stream));
+  DevBuf<char> tmp;
+  NXFX_CUDA(ctx, tmp.alloc(tmp_bytes));
+  NXFX_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, len.p, ctx->rowptr.p, n + 1, ctx->stream));
+  ctx->launches++;
+  int32_t nnz = 0;
+  NXFX_CUDA(ctx, cudaMemcpyAsync(&nnz, ctx->rowptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  NXFX_REQUIRE(ctx, nnz > 0, "pattern overflow (nnz does not fit int32)");
+  ctx->nnz = nnz;
+  NXFX_CUDA(ctx, ctx->colidx.alloc((size_t)nnz));
+  NXFX_CUDA(ctx, ctx->vals.alloc((size_t)nnz));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->vals.p, 0, (size_t)nnz * sizeof(double), ctx->stream));
+  NXFX_LAUNCH(ctx, fill_cols_kernel, (int)cdiv(n, kThreads), kThreads, 0, g, ctx->rowptr.p, ctx->colidx.p);
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->has_pattern = true;
+  ctx->assembled = false;
+  return NXFX_OK;
+}
+
+int nxfx_csr_device(nxfx_ctx* ctx, const int32_t** rowptr, const int32_t** colidx, double** vals) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
+  if (rowptr) *rowptr = ctx->rowptr.p;
+  if (colidx) *colidx = ctx->colidx.p;
+  if (vals) *vals = ctx->vals.p;
+  return NXFX_OK;
+}
+
+// ---- (3) numeric ---------------------------------------------------------------------------------
+int nxfx_assemble(nxfx_ctx* ctx, const double* pbc, const double* R_cell, double R_const,
+                  const double* f_cell, double f_const, int lhs, int rhs, int accumulate, double* b) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
+  NXFX_REQUIRE(ctx, !rhs || (b && pbc), "rhs requested without b / p_bc");
+  if (!lhs && !rhs) return NXFX_OK;
+  Net g = make_net(ctx);
+  Coef c;
+  c.pbc = pbc; c.R_cell = R_cell; c.f_cell = f_cell; c.R_const = R_const; c.f_const = f_const;
+  c.cell_rh = ctx->cell_rh.p;
+  const int grid = (int)cdiv(ctx->ndofs, kTileRows);
+  if (accumulate)
+    NXFX_LAUNCH(ctx, assemble_rows_kernel<true>, grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs);
+  else
+    NXFX_LAUNCH(ctx, assemble_rows_kernel<false>, grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs);
+  if (lhs) { ctx->assembled = true; ctx->pc_ready = false; }
+  return NXFX_OK;
+}
+
+// ---- (4) solve -----------------------------------------------------------------------------------
+int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t* t_parent,
+                           const int32_t* t_pedge, const int32_t* t_cptr, const int32_t* t_cidx,
+                           int32_t n_chunks, const int32_t* chunk_lptr, int32_t n_lvl_ptr,
+                           const int32_t* lvl_ptr, int32_t n_chords, const int32_t* chord_edge) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_network, "no network");
+  auto& s = ctx->tree;
+  s.set = false;
+  const size_t nb = (size_t)ctx->n_bif;
+  if (nb == 0) { s.n_chunks = 0; s.set = true; return NXFX_OK; }
+  NXFX_REQUIRE(ctx, t_of_bif && t_parent && t_pedge && t_cptr && chunk_lptr && lvl_ptr && n_chunks >= 1, "null input");
+  NXFX_REQUIRE(ctx, chunk_lptr[0] == 0 && chunk_lptr[n_chunks] == n_lvl_ptr - 1 && lvl_ptr[0] == 0 &&
+                        lvl_ptr[n_lvl_ptr - 1] == ctx->n_bif, "inconsistent level tables");
+  for (size_t t = 0; t < nb; ++t) {
+    if (t_parent[t] >= (int32_t)nb || t_pedge[t] >= ctx->E || (t_parent[t] >= 0) != (t_pedge[t] >= 0))
+      return fail(ctx, NXFX_ERR_INVALID, "tree schedule: bad parent at %zu", t);
+  }
+  int rc;
+  if ((rc = upload(ctx, s.t_of_bif, t_of_bif, nb))) return rc;
+  if ((rc = upload(ctx, s.t_parent, t_parent, nb))) return rc;
+  if ((rc = upload(ctx, s.t_pedge, t_pedge, nb))) return rc;
+  if ((rc = upload(ctx, s.t_cptr, t_cptr, nb + 1))) return rc;
+  if ((rc = upload(ctx, s.t_cidx, t_cidx, (size_t)t_cptr[nb]))) return rc;
+  if ((rc = upload(ctx, s.chunk_lptr, chunk_lptr, (size_t)n_chunks + 1))) return rc;
+  if ((rc = upload(ctx, s.lvl_ptr, lvl_ptr, (size_t)n_lvl_ptr))) return rc;
+  if ((rc = upload(ctx, s.chord_edge, chord_edge, (size_t)std::max(0, n_chords)))) return rc;
+  s.n_chunks = n_chunks; s.n_lvl_ptr = n_lvl_ptr; s.n_chords = n_chords;
+  NXFX_CUDA(ctx, s.diag0.alloc(nb));
+  NXFX_CUDA(ctx, s.d.alloc(nb));
+  NXFX_CUDA(ctx, s.gd.alloc(nb));
+  NXFX_CUDA(ctx, s.r.alloc(nb));
+  NXFX_CUDA(ctx, s.lam.alloc(nb));
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  s.set = true;
+  ctx->pc_ready = false;
+  return NXFX_OK;
+}
+
+int nxfx_pc_setup(nxfx_ctx* ctx) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  return do_pc_setup(ctx);
+}
+
+int nxfx_pc_apply(nxfx_ctx* ctx, const double* r, double* z) {
+  if (!ctx || !r || !z) return NXFX_ERR_INVALID;
+  return do_pc_apply(ctx, NXFX_PC_NETWORK_SCHUR, r, z);
+}
+
+int nxfx_spmv(nxfx_ctx* ctx, const double* x, double* y) {
+  if (!ctx || !x || !y) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
+  return do_spmv(ctx, x, y);
+}
+
+int nxfx_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, double* norm2) {
+  if (!ctx || !b || !x || !r) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
+  int rc = do_residual(ctx, b, x, r, slot(ctx, 0));
+  if (rc) return rc;
+  if (norm2) {
+    NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, slot(ctx, 0), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *norm2 = ctx->scal_h[0];
+  }
+  return NXFX_OK;
+}
+
+int nxfx_solve(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts* opts, nxfx_solve_info* info) {
+  if (!ctx || !b || !x || !opts || !info) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->assembled, "matrix has not been assembled");
+  std::memset(info, 0, sizeof *info);
+  int rc;
+  if (opts->pc_type == NXFX_PC_NETWORK_SCHUR && !ctx->pc_ready)
+    if ((rc = do_pc_setup(ctx))) return rc;
+  if (opts->ksp_type == NXFX_KSP_PREONLY) rc = solve_preonly(ctx, b, x, opts, info);
+  else if (opts->ksp_type == NXFX_KSP_FGMRES) rc = solve_fgmres(ctx, b, x, opts, info);
+  else return fail(ctx, NXFX_ERR_UNSUPPORTED, "unknown ksp_type %d", opts->ksp_type);
+  if (rc) return rc;
+  if (!info->converged && opts->error_if_not_converged)
+    return fail(ctx, NXFX_ERR_NOT_CONVERGED, "linear solve did not converge: ||r|| = %.3e, ||b|| = %.3e after %d iterations",
+                info->residual_norm, info->rhs_norm, info->iterations);
+  return NXFX_OK;
+}
+
+// ---- (5) end-to-end host-buffer step ---------------------------------------------------------------
+int nxfx_assemble_solve_host(nxfx_ctx* ctx, const double* node_pos, const double* pbc_vertex,
+                             double R_const, double f_const, const nxfx_solve_opts* opts, double* x_h,
+                             nxfx_solve_info* info) {
+  if (!ctx || !node_pos || !pbc_vertex || !opts || !x_h || !info) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
+  const size_t n = (size_t)ctx->ndofs;
+  if (ctx->e2e_b.n < n) {
+    NXFX_CUDA(ctx, ctx->e2e_b.alloc(n));
+    NXFX_CUDA(ctx, ctx->e2e_x.alloc(n));
+    NXFX_CUDA(ctx, ctx->e2e_pbc.alloc((size_t)ctx->nv));
+  }
+  int rc;
+  if ((rc = nxfx_update_node_positions(ctx, node_pos))) return rc;
+  NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->e2e_pbc.p, pbc_vertex, (size_t)ctx->nv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = nxfx_assemble(ctx, ctx->e2e_pbc.p, nullptr, R_const, nullptr, f_const, 1, 1, 0, ctx->e2e_b.p))) return rc;
+  if ((rc = nxfx_solve(ctx, ctx->e2e_b.p, ctx->e2e_x.p, opts, info))) return rc;
+  NXFX_CUDA(ctx, cudaMemcpyAsync(x_h, ctx->e2e_x.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NXFX_OK;
+}
+
+int nxfx_global_flux(nxfx_ctx* ctx, const double* x, double* out) {
+  if (!ctx || !x || !out) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_network, "no network");
+  NXFX_LAUNCH(ctx, global_flux_kernel, vec_grid(ctx, ctx->nc), kThreads, 0, make_net(ctx), x, out);
+  return NXFX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+// Network Schur-complement preconditioner (replaces PCLU/MUMPS, solver.py:58-65).
+//
+// The saddle-point operator of assembly.py:253-277 is condensed exactly, graph edge by graph
+// edge, onto the bifurcation multipliers:
+//   pressure rows   q_{a+1} - q_a = r_p[a]              =>  q_a = q_0 + F_a   (prefix sums F)
+//   sum of the flux rows of an edge (pressure telescopes)
+//                   W q_0 + w.F + lam_v - lam_u = sum r_q =>  q_0 = g (c + lam_u - lam_v)
+//                   (w = row sums of the edge mass matrix, W = sum w = sum_j R_j h_j, g = 1/W)
+//   multiplier rows => weighted graph Laplacian  L lam = rhs  with conductances g.
+// On a tree network L is eliminated leaf -> root without fill; the tree is cut into chunks
+// (subtrees) that one thread block solves level by level, plus one top chunk.  Graph edges that
+// close a cycle ("chords") keep their conductance on the diagonal only, so P is then an SPD
+// support-graph approximation and the outer FGMRES absorbs the difference.
+// Back-substitution restores q by the prefix sums and p by the flux-row recurrence.
+// P is built from cell_rh = R*h written by the assembly kernel, i.e. from the same element data
+// as A; P^{-1} A = I up to rounding on forests.
+#pragma once
+
+#include "assemble.cuh"
+
+namespace nxfx {
+
+struct TreeDev {
+  const int32_t* __restrict__ t_of_bif;
+  const int32_t* __restrict__ t_parent;
+  const int32_t* __restrict__ t_pedge;
+  const int32_t* __restrict__ t_cptr;
+  const int32_t* __restrict__ t_cidx;
+  const int32_t* __restrict__ chunk_lptr;
+  const int32_t* __restrict__ lvl_ptr;
+  double* diag0;
+  double* d;
+  double* gd;
+  double* r;
+  double* lam;
+};
+
+// g_e = 1 / sum_j R_j h_j
+__global__ void __launch_bounds__(kThreads)
+edge_conductance_kernel(int E, int N, const double* __restrict__ cell_rh, double* __restrict__ g) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  double W = 0.0;
+  for (int j = 0; j < N; ++j) W += cell_rh[(size_t)e * N + j];
+  g[e] = 1.0 / W;
+}
+
+__global__ void __launch_bounds__(kThreads)
+bif_diag_kernel(Net g, TreeDev t, const double* __restrict__ edge_g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n_bif) return;
+  double s = 0.0;
+  for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) s += edge_g[g.bif_inc[k] >> 1];
+  t.diag0[t.t_of_bif[i]] = s;
+}
+
+// MODE 0: numeric factorisation  d_t = diag0_t - sum_c g_c^2/d_c ; gd_t = g_t/d_t
+// MODE 1: forward (leaf -> root)  r_t += sum_c gd_c r_c
+// MODE 2: backward (root -> leaf) lam_t = r_t/d_t + gd_t lam_parent
+// MODE 3: forward then backward (top chunk)
+// One thread block per chunk; chunk = blockIdx.x + chunk0.
+template <int MODE>
+__global__ void __launch_bounds__(1024)
+tree_sweep_kernel(TreeDev t, const double* __restrict__ edge_g, int chunk0) {
+  const int chunk = chunk0 + blockIdx.x;
+  const int L0 = t.chunk_lptr[chunk], L1 = t.chunk_lptr[chunk + 1];
+  if (MODE == 0 || MODE == 1 || MODE == 3) {
+    for (int L = L1 - 1; L >= L0; --L) {
+      const int b = t.lvl_ptr[L], e = t.lvl_ptr[L + 1];
+      for (int n = b + threadIdx.x; n < e; n += blockDim.x) {
+        const int c0 = t.t_cptr[n], c1 = t.t_cptr[n + 1];
+        if (MODE == 0) {
+          double dd = t.diag0[n];
+          for (int k = c0; k < c1; ++k) {
+            const int c = t.t_cidx[k];
+            dd -= edge_g[t.t_pedge[c]] * t.gd[c];
+          }
+          t.d[n] = dd;
+          const int pe = t.t_pedge[n];
+          t.gd[n] = pe >= 0 ? edge_g[pe] / dd : 0.0;
+        } else {
+          double rr = t.r[n];
+          for (int k = c0; k < c1; ++k) {
+            const int c = t.t_cidx[k];
+            rr += t.gd[c] * t.r[c];
+          }
+          t.r[n] = rr;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (MODE == 2 || MODE == 3) {
+    for (int L = L0; L < L1; ++L) {
+      const int b = t.lvl_ptr[L], e = t.lvl_ptr[L + 1];
+      for (int n = b + threadIdx.x; n < e; n += blockDim.x) {
+        const int p = t.t_parent[n];
+        double v = t.r[n] / t.d[n];
+        if (p >= 0) v += t.gd[n] * t.lam[p];
+        t.lam[n] = v;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Edge condensation: c_e = sum r_q - w.F,  F_N = sum r_p
+__global__ void __launch_bounds__(kThreads)
+edge_condense_kernel(Net g, const double* __restrict__ cell_rh, const double* __restrict__ r,
+                     double* __restrict__ edge_c, double* __restrict__ edge_fn) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.E) return;
+  const int N = g.N;
+  const double* rq = r + (size_t)g.edge_slot[e] * (N + 1);
+  const double* rp = r + g.poff + (size_t)e * N;
+  const double* rh = cell_rh + (size_t)e * N;
+  double s = 0.0, F = 0.0, wF = 0.0, hl = 0.0;
+  for (int a = 0; a <= N; ++a) {
+    s += rq[a];
+    const double hr = a < N ? rh[a] : 0.0;
+    wF += 0.5 * (hl + hr) * F;
+    if (a < N) F += rp[a];
+    hl = hr;
+  }
+  edge_c[e] = s - wF;
+  edge_fn[e] = F;
+}
+
+// rhs_b = -r_lam + sum_in (F_N + g c) - sum_out g c      (schedule order)
+__global__ void __launch_bounds__(kThreads)
+bif_rhs_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* __restrict__ edge_g,
+               const double* __restrict__ edge_c, const double* __restrict__ edge_fn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n_bif) return;
+  double s = -r[g.loff + i];
+  for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) {
+    const int inc = g.bif_inc[k], e = inc >> 1;
+    const double gc = edge_g[e] * edge_c[e];
+    s += (inc & 1) ? (edge_fn[e] + gc) : -gc;
+  }
+  t.r[t.t_of_bif[i]] = s;
+}
+
+// Back-substitution: q_a = q_0 + F_a ; p_0 = r_q0 + lam_u - (Mq)_0 ; p_a = p_{a-1} + r_qa - (Mq)_a
+__global__ void __launch_bounds__(kThreads)
+edge_backsub_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh,
+                    const double* __restrict__ r, const double* __restrict__ edge_g,
+                    const double* __restrict__ edge_c, double* __restrict__ z) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.E) {
+    const int i = idx - g.E;
+    if (i < g.n_bif) z[g.loff + i] = t.lam[t.t_of_bif[i]];
+    return;
+  }
+  const int e = idx, N = g.N;
+  const int slot = g.edge_slot[e];
+  const int4 uv = g.slot_uvl[slot];
+  const double lu = uv.z >= 0 ? t.lam[t.t_of_bif[uv.z]] : 0.0;
+  const double lv = uv.w >= 0 ? t.lam[t.t_of_bif[uv.w]] : 0.0;
+  const double* rq = r + (size_t)slot * (N + 1);
+  const double* rp = r + g.poff + (size_t)e * N;
+  const double* rh = cell_rh + (size_t)e * N;
+  double* zq = z + (size_t)slot * (N + 1);
+  double* zp = z + g.poff + (size_t)e * N;
+  const double q0 = edge_g[e] * (edge_c[e] + lu - lv);
+  double F = 0.0, qprev = 0.0, qa = q0, hl = 0.0, p = lu;
+  for (int a = 0; a <= N; ++a) {
+    zq[a] = qa;
+    double qn = 0.0, hr = 0.0;
+    if (a < N) {
+      F += rp[a];
+      qn = q0 + F;
+      hr = rh[a];
+      const double Mq = hl * (qprev * kSixth + qa * kThird) + hr * (qa * kThird + qn * kSixth);
+      p += rq[a] - Mq;
+      zp[a] = p;
+    }
+    qprev = qa;
+    qa = qn;
+    hl = hr;
+  }
+}
+
+// z = D^{-1} r on flux rows (D = diag of the mass block), identity elsewhere
+__global__ void __launch_bounds__(kThreads)
+jacobi_flux_kernel(int n, int nq, const int32_t* __restrict__ rowptr,
+                   const int32_t* __restrict__ colidx, const double* __restrict__ vals,
+                   const double* __restrict__ r, double* __restrict__ z) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = r[i];
+  if (i < nq) {
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      if (colidx[k] == i) v /= vals[k];
+  }
+  z[i] = v;
+}
+
+}  // namespace nxfx

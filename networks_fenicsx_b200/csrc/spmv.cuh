@@ -1,0 +1,182 @@
+// CSR SpMV and fused vector kernels for the Krylov solve (solver.py:127 replaces KSPSolve).
+//
+// SpMV is the CSR-stream form: a block owns kTileRows consecutive rows, streams the tile's
+// (value, column) pairs from HBM with fully coalesced loads (8 independent loads per thread in
+// flight), gathers x from L2 (x is 8*n_dofs bytes, far below the 126 MB L2), parks the products
+// in shared memory and reduces each row sequentially in ascending column order.  The row sum is
+// therefore deterministic and bit-identical to a sequential CSR product (mul then add, no FMA).
+// The residual variant fuses r = b - A x and the block partial of ||r||^2 into the same pass.
+#pragma once
+
+#include "ctx.cuh"
+
+namespace nxfx {
+
+constexpr int kEntriesPerThread = kTileCap / kTileRows;  // 8
+constexpr int kMaxPartials = 4096;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum (fixed tree => deterministic); result valid in thread 0.
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* red /* [THREADS/32] */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (w == 0) {
+    s = lane < THREADS / 32 ? red[lane] : 0.0;
+    s = warp_sum(s);
+  }
+  __syncthreads();
+  return s;
+}
+
+// Last-block-done final reduction of per-block partials -> out[0..K).  Deterministic: the last
+// block (whichever it is) sums the partials in index order with the same fixed tree.
+template <int THREADS, int K>
+__device__ __forceinline__ void finish_partials(double (&mine)[K], double* partial, int nblocks,
+                                                unsigned int* ticket, double* out, double* red) {
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) partial[(size_t)k * kMaxPartials + blockIdx.x] = mine[k];
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    last = (t == (unsigned int)nblocks - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += THREADS)
+      s += ((volatile double*)partial)[(size_t)k * kMaxPartials + i];
+    s = block_sum<THREADS>(s, red);
+    if (threadIdx.x == 0) out[k] = s;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// MODE 0: y = A x.   MODE 1: y = b - A x, block partials of ||y||^2 -> norm2_out (grid-strided
+// tiles so that the partial count stays bounded).
+template <int MODE>
+__global__ void __launch_bounds__(kTileRows)
+spmv_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
+            const int32_t* __restrict__ colidx, const double* __restrict__ vals,
+            const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
+            double* partial, unsigned int* ticket, double* norm2_out) {
+  __shared__ double sm[kTileCap];
+  __shared__ int srow[kTileRows + 1];
+  __shared__ double red[kTileRows / 32];
+  double nrm = 0.0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * kTileRows;
+    const int nr = min(kTileRows, n - r0);
+    if (threadIdx.x <= nr) srow[threadIdx.x] = rowptr[r0 + threadIdx.x];
+    if (threadIdx.x == 0) srow[nr] = rowptr[r0 + nr];
+    __syncthreads();
+    const int sbase = srow[0];
+    const int tnnz = srow[nr] - sbase;
+    const bool valid = threadIdx.x < nr;
+    const int rs = valid ? srow[threadIdx.x] - sbase : 0;
+    const int re = valid ? srow[threadIdx.x + 1] - sbase : 0;
+    double acc = 0.0;
+    for (int c0 = 0; c0 < tnnz; c0 += kTileCap) {
+      const int cnt = min(kTileCap, tnnz - c0);
+      const size_t g0 = (size_t)sbase + c0;
+      double v[kEntriesPerThread];
+      int c[kEntriesPerThread];
+#pragma unroll
+      for (int k = 0; k < kEntriesPerThread; ++k) {
+        const int idx = threadIdx.x + k * kTileRows;
+        if (idx < cnt) {
+          v[k] = __ldg(vals + g0 + idx);
+          c[k] = __ldg(colidx + g0 + idx);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kEntriesPerThread; ++k) {
+        const int idx = threadIdx.x + k * kTileRows;
+        if (idx < cnt) sm[idx] = __dmul_rn(v[k], x[c[k]]);
+      }
+      __syncthreads();
+      const int s = max(rs - c0, 0), e = min(re - c0, cnt);
+      for (int k = s; k < e; ++k) acc = __dadd_rn(acc, sm[k]);
+      __syncthreads();
+    }
+    if (valid) {
+      if (MODE == 0) {
+        y[r0 + threadIdx.x] = acc;
+      } else {
+        const double r = __dsub_rn(b[r0 + threadIdx.x], acc);
+        y[r0 + threadIdx.x] = r;
+        nrm += r * r;
+      }
+    }
+  }
+  if (MODE == 1) {
+    double mine[1] = {block_sum<kTileRows>(nrm, red)};
+    finish_partials<kTileRows, 1>(mine, partial, gridDim.x, ticket, norm2_out, red);
+  }
+}
+
+// ---- vector kernels --------------------------------------------------------------------------
+// out[k] = <a_k, w>, k < K, a_k = A + k*stride (one pass over w)
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+multi_dot_kernel(int n, const double* __restrict__ A, size_t stride, const double* __restrict__ w,
+                 double* partial, unsigned int* ticket, double* out) {
+  __shared__ double red[kThreads / 32];
+  double acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double wi = w[i];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] += A[(size_t)k * stride + i] * wi;
+  }
+  double mine[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) mine[k] = block_sum<kThreads>(acc[k], red);
+  finish_partials<kThreads, K>(mine, partial, gridDim.x, ticket, out, red);
+}
+
+// w += sum_k sign * h[k] * a_k
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+multi_axpy_kernel(int n, const double* __restrict__ A, size_t stride, const double* __restrict__ h,
+                  double sign, double* __restrict__ w) {
+  double hk[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) hk[k] = sign * h[k];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double wi = w[i];
+#pragma unroll
+    for (int k = 0; k < K; ++k) wi += hk[k] * A[(size_t)k * stride + i];
+    w[i] = wi;
+  }
+}
+
+// y = x * (1 / sqrt(*norm2))   (normalise a Krylov vector with a device-side norm)
+__global__ void __launch_bounds__(kThreads)
+scale_by_inv_norm_kernel(int n, const double* __restrict__ x, const double* norm2,
+                         double* __restrict__ y) {
+  const double s = 1.0 / sqrt(*norm2);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    y[i] = x[i] * s;
+}
+
+__global__ void __launch_bounds__(kThreads)
+add_kernel(int n, const double* __restrict__ z, double* __restrict__ x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    x[i] += z[i];
+}
+
+}  // namespace nxfx

@@ -1,0 +1,70 @@
+"""Shared graph builders / comparison helpers for the tests."""
+
+import networkx as nx
+import numpy as np
+
+from oracle import reference_port as rp
+
+
+def edge_info_graph():
+    """The 8-node cyclic graph of the reference's tests/test_edge_info.py:12-33."""
+    G = nx.DiGraph()
+    G.add_node(0, pos=np.zeros(3))
+    G.add_node(1, pos=np.array([0.0, 0.0, 1.0]))
+    G.add_node(2, pos=np.array([0.2, 0.2, 2.0]))
+    G.add_node(3, pos=np.array([-0.2, 0.3, 2.0]))
+    G.add_node(4, pos=np.array([0.0, 0.1, 2.1]))
+    G.add_node(5, pos=np.array([0.1, -0.1, 3.0]))
+    G.add_node(6, pos=np.array([-0.3, 0.4, 4.0]))
+    G.add_node(7, pos=1.1 * G.nodes[1]["pos"])
+    for e in [(0, 1), (1, 7), (7, 2), (2, 5), (7, 3), (3, 4), (4, 5), (7, 4), (5, 6)]:
+        G.add_edge(*e)
+    return G
+
+
+def linear_graph(n: int, dim: int = 2, ordered=lambda _: True) -> nx.DiGraph:
+    """tests/test_orientation.py:10-25 of the reference."""
+    G = nx.DiGraph()
+    G.add_nodes_from(range(n))
+    for i in range(n - 1):
+        if ordered(i):
+            G.add_edge(i, i + 1)
+        else:
+            G.add_edge(i + 1, i)
+    for i in range(n):
+        pos = np.zeros(dim)
+        pos[0] = i / (n - 1)
+        G.nodes[i]["pos"] = pos
+    return G
+
+
+def double_junction_graph():
+    """Two junctions: 0->1, 1->2, 1->3, 3->4, 3->5 (SURVEY 8d note on the 'double Y' config)."""
+    G = nx.DiGraph()
+    pts = [(0, 0, 0), (0, 1, 0), (-1, 2, 0), (1, 2, 0), (0.5, 3, 0.2), (1.7, 3.1, -0.1)]
+    for i, p in enumerate(pts):
+        G.add_node(i, pos=np.array(p, dtype=float))
+    for e in [(0, 1), (1, 2), (1, 3), (3, 4), (3, 5)]:
+        G.add_edge(*e)
+    return G
+
+
+def random_tree(n_nodes: int, seed: int, dim: int = 3):
+    """Random recursive tree with node 0 as single inlet of degree 1, random edge directions off."""
+    rng = np.random.default_rng(seed)
+    G = nx.DiGraph()
+    for i in range(n_nodes):
+        G.add_node(i, pos=rng.normal(size=dim))
+    G.add_edge(0, 1)
+    for k in range(2, n_nodes):
+        G.add_edge(int(rng.integers(1, k)), k)
+    return G
+
+
+def oracle_for(nm, N):
+    """OracleNetwork on the same arrays the product mesh was built from."""
+    return rp.OracleNetwork(nm._node_pos, nm.graph_edges, nm.edge_colors, N)
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))

@@ -1,0 +1,221 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): sparsity pattern and indexing bit-exact; matrix entries within
+1e-12 relative (here: bit-exact, the kernels avoid FMA contraction); solution within 1e-8 relative
+L2 of the direct solve (here: 1e-10).
+"""
+
+import networkx as nx
+import numpy as np
+import pytest
+
+import networks_fenicsx_b200 as nxfx
+from networks_fenicsx_b200 import network_generation as ng
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+P_Y = lambda x: x[1]  # noqa: E731
+P_X = lambda x: x[0]  # noqa: E731
+
+
+def run_case(G, N, strategy, p_bc, R=None, f=None, kind=None, petsc_options=None):
+    nm = nxfx.NetworkMesh(G, N=N, color_strategy=strategy)
+    asm = nxfx.HydraulicNetworkAssembler(nm)
+    asm.compute_forms(p_bc_ex=p_bc, R=R, f=f)
+    solver = nxfx.Solver(asm, kind=kind, petsc_options=petsc_options)
+    solver.assemble()
+    sol = solver.solve()
+    net = helpers.oracle_for(nm, N)
+    A, b = net.assemble(net.eval_pbc(p_bc), R=1.0 if R is None else R, f=0.0 if f is None else f)
+    return nm, asm, solver, sol, net, A, b
+
+
+def check_system(solver, net, A, b, exact=True):
+    rp_, ci, va = solver.A.getValuesCSR()
+    assert np.array_equal(rp_, A.indptr), "row pointers differ"
+    assert np.array_equal(ci, A.indices), "column indices differ"
+    assert A.nnz == net.expected_nnz()
+    if exact:
+        assert np.array_equal(va, A.data)
+        assert np.array_equal(solver.b.array_r, b)
+    else:
+        np.testing.assert_allclose(va, A.data, rtol=1e-12, atol=0)
+        np.testing.assert_allclose(solver.b.array_r, b, rtol=1e-12, atol=1e-300)
+
+
+def check_solution(sol, net, A, b, tol=1e-10):
+    x_ref = net.solve(A, b)
+    x = np.concatenate([f.x.array for f in sol])
+    assert helpers.rel_l2(x, x_ref) < tol
+    return x, x_ref
+
+
+@pytest.mark.parametrize("N", [1, 2, 4, 7])
+@pytest.mark.parametrize("strategy", [None, "smallest_last", "largest_first"])
+def test_y_bifurcation(N, strategy):
+    """configs[0]: demos/demo_Y_bifurcation.py (make_tree(2,1,3), p_bc = y)."""
+    G = ng.make_tree(2, 1, 3)
+    nm, asm, solver, sol, net, A, b = run_case(G, N, strategy, P_Y)
+    check_system(solver, net, A, b)
+    check_solution(sol, net, A, b)
+    assert [f.name for f in sol] == [f"flux_color_{i}" for i in range(nm.num_edge_colors)] + ["pressure", "global_flux"]
+
+
+def test_y_bifurcation_known_answer():
+    """SURVEY A.6 KAT: q = (0.77485177.., 0.38742588.., 0.38742588..), lambda = -0.38742588.."""
+    G = ng.make_tree(2, 1, 3)
+    nm, asm, solver, sol, net, A, b = run_case(G, 4, None, P_Y)
+    q = [f.x.array for f in sol[:3]]
+    np.testing.assert_allclose(q[0], 0.7748517734455862, rtol=1e-12)
+    np.testing.assert_allclose(q[1], 0.3874258867227931, rtol=1e-12)
+    np.testing.assert_allclose(q[2], 0.3874258867227931, rtol=1e-12)
+    np.testing.assert_allclose(sol[-1].x.array, [-0.3874258867227931], rtol=1e-12)
+    np.testing.assert_allclose(
+        sol[-2].x.array[:4], [-0.04842824, -0.14528471, -0.24214118, -0.33899765], atol=1e-8
+    )
+
+
+def test_double_y_demo():
+    """configs[1]: demos/demo_double_Y_bifurcation.py (make_tree(2,3.1,7.3), N=5, p_bc = x)."""
+    G = ng.make_tree(2, 3.1, 7.3)
+    nm, asm, solver, sol, net, A, b = run_case(G, 5, None, P_X)
+    check_system(solver, net, A, b)
+    x, x_ref = check_solution(sol, net, A, b)
+    np.testing.assert_allclose(sol[1].x.array, -0.920444352, atol=1e-8)
+    np.testing.assert_allclose(sol[2].x.array, 0.920444352, atol=1e-8)
+    np.testing.assert_allclose(sol[0].x.array, 0.0, atol=1e-12)
+
+
+def test_two_junctions():
+    G = helpers.double_junction_graph()
+    nm, asm, solver, sol, net, A, b = run_case(G, 6, "largest_first", lambda x: x[1] + 0.3 * x[0])
+    check_system(solver, net, A, b)
+    check_solution(sol, net, A, b)
+
+
+@pytest.mark.parametrize("n,N", [(10, 1), (10, 4), (10, 16), (7, 64)])
+def test_tree(n, N):
+    """configs[2]: binary tree, 10 generations, refined edges (demo_tree / demo_perf protocol)."""
+    G = ng.make_tree(n, n, n)
+    nm, asm, solver, sol, net, A, b = run_case(G, N, "smallest_last", P_Y)
+    check_system(solver, net, A, b)
+    x, x_ref = check_solution(sol, net, A, b)
+    # closed form: resistor network with boundary pressures -p_bc
+    q_edge, lam = net.resistor_network_solution(net.eval_pbc(P_Y))
+    np.testing.assert_allclose(sol[-1].x.array, lam, rtol=1e-9, atol=1e-12)
+    qs = np.concatenate([f.x.array for f in sol[:-2]])
+    q_first = qs[net.fb]
+    np.testing.assert_allclose(q_first, q_edge, rtol=1e-8, atol=1e-11)
+
+
+def test_demo_tree_refinement():
+    """demos/demo_tree.py: make_tree(2,1,1) refined to N=1024, kind='mpi'."""
+    G = ng.make_tree(2, 1, 1)
+    for N in (2, 64, 1024):
+        nm, asm, solver, sol, net, A, b = run_case(G, N, None, P_Y, kind="mpi")
+        check_system(solver, net, A, b)
+        check_solution(sol, net, A, b)
+        gq = nxfx.post_processing.extract_global_flux(nm, sol)
+        x = np.concatenate([f.x.array for f in sol])
+        assert np.array_equal(gq.x.array, net.global_flux(x))
+
+
+def test_arterial_tree_nest():
+    """configs[3]: demos/demo_arterial_tree.py (N=5 generations, 40 cells/edge, largest_first,
+    kind='nest'), plus radius-dependent resistance R_e = 8 mu / (pi r_e^4)."""
+    G = ng.make_arterial_tree(N=5, direction=np.array([0.1, 1, 0]))
+    nm, asm, solver, sol, net, A, b = run_case(G, 40, nx.coloring.strategy_largest_first, P_Y, kind="nest")
+    assert solver.A.getType() == "nest"
+    check_system(solver, net, A, b)
+    check_solution(sol, net, A, b)
+    assert net.n_dofs == 2526 and A.nnz == 8891
+    blk = solver.A.getNestSubMatrix(0, 0)
+    assert blk.shape == (asm.block_sizes[0],) * 2
+    radius = np.array([G.edges[e]["radius"] for e in G.edges()])
+    R_edge = 8.0 * 1.0 / (np.pi * radius**4)
+    nm, asm, solver, sol, net, A, b = run_case(G, 40, "largest_first", P_Y, R=np.repeat(R_edge, 40))
+    check_system(solver, net, A, b)
+    check_solution(sol, net, A, b)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_tree_with_source(seed):
+    G = helpers.random_tree(200, seed)
+    rng = np.random.default_rng(seed)
+    N = 3
+    nc = N * G.number_of_edges()
+    R = rng.uniform(0.5, 2.0, nc)
+    f = rng.normal(size=nc)
+    nm, asm, solver, sol, net, A, b = run_case(G, N, "smallest_last", lambda x: x[0] - 2 * x[2], R=R, f=f)
+    check_system(solver, net, A, b)
+    check_solution(sol, net, A, b)
+
+
+def test_cyclic_graph_solve():
+    """tests/test_edge_info.py graph (cycles, degree-4 node): the Schur preconditioner is a
+    spanning-tree approximation there; FGMRES must still reach the direct solution."""
+    G = helpers.edge_info_graph()
+    nm, asm, solver, sol, net, A, b = run_case(G, 10, None, lambda x: x[2])
+    check_system(solver, net, A, b)
+    check_solution(sol, net, A, b, tol=1e-9)
+    assert not solver._schedule.is_forest
+
+
+def test_orientation_and_counts():
+    """tests/test_orientation.py + tests/test_make_tree.py of the reference on device vertices."""
+    for order, ordered in (("in", lambda _: True), ("reverse", lambda _: False), ("alt", lambda k: k % 2)):
+        for N in (1, 4, 8):
+            G = helpers.linear_graph(30, ordered=ordered)
+            nm = nxfx.NetworkMesh(G, N=N)
+            val = nm.oriented_tangent_integral((1, 0))
+            expected = {"in": 1.0, "reverse": -1.0, "alt": (29 % 2) * -1 / 29}[order]
+            assert np.isclose(val, expected)
+            net = helpers.oracle_for(nm, N)
+            assert np.array_equal(nm.mesh.geometry.x, net.x3), "device vertices differ from mesh.py:290"
+
+
+def test_spmv_and_krylov_options():
+    G = ng.make_tree(8, 8, 8)
+    nm, asm, solver, sol, net, A, b = run_case(G, 3, "smallest_last", P_Y)
+    rng = np.random.default_rng(0)
+    xv = solver.x.duplicate()
+    yv = solver.x.duplicate()
+    xh = rng.normal(size=net.n_dofs)
+    xv.array[:] = xh
+    solver.A.mult(xv, yv)
+    assert np.array_equal(yv.array_r, A @ xh), "SpMV is not bit-identical to a sequential CSR product"
+    x_ref = net.solve(A, b)
+    for opts in (
+        {"ksp_type": "gmres", "pc_type": "lu", "ksp_rtol": 1e-12},
+        {"ksp_type": "gmres", "pc_type": "jacobi", "ksp_rtol": 1e-12, "ksp_gmres_restart": 100, "ksp_max_it": 3000},
+    ):
+        s2 = nxfx.Solver(asm, petsc_options=opts)
+        s2.assemble()
+        sol2 = s2.solve()
+        x = np.concatenate([f.x.array for f in sol2])
+        assert helpers.rel_l2(x, x_ref) < 1e-8, (opts, s2.ksp.getIterationNumber())
+
+
+def test_accumulate_semantics_and_errors():
+    G = ng.make_tree(4, 1, 1)
+    nm = nxfx.NetworkMesh(G, N=2, color_strategy="smallest_last")
+    asm = nxfx.HydraulicNetworkAssembler(nm)
+    with pytest.raises(RuntimeError):
+        asm.assemble()
+    asm.compute_forms(p_bc_ex=P_Y)
+    A, b = asm.assemble()
+    va1 = A.getValuesCSR()[2].copy()
+    b1 = b.array_r.copy()
+    asm.assemble(A, b)  # ADD_VALUES into non-zeroed targets (assembly.py:355,362)
+    assert np.array_equal(A.getValuesCSR()[2], 2 * va1)
+    assert np.array_equal(b.array_r, 2 * b1)
+    A.zeroEntries()
+    b.zeroEntries()
+    asm.assemble(A, b)
+    assert np.array_equal(A.getValuesCSR()[2], va1) and np.array_equal(b.array_r, b1)
+    solver = nxfx.Solver(asm, petsc_options={"ksp_type": "gmres", "pc_type": "none", "ksp_max_it": 2,
+                                             "ksp_rtol": 1e-14, "ksp_error_if_not_converged": True})
+    solver.assemble()
+    with pytest.raises(RuntimeError, match="did not converge"):
+        solver.solve()
