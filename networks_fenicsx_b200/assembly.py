@@ -170,7 +170,9 @@ class HydraulicNetworkAssembler:
             x = nm.mesh.geometry.x
             pbc = np.ascontiguousarray(np.asarray(fn(x.T), dtype=np.float64) * np.ones(nv))
         self._pbc_host = pbc
-        self._pbc_d = dev.from_host(pbc)
+        if self._pbc_d is None or self._pbc_d.n != pbc.size:
+            self._pbc_d = dev.empty(pbc.size)
+        self._pbc_d.upload(pbc)
         self._R = self._coefficient(R, 1.0, nc, "R")
         self._f = self._coefficient(f, 0.0, nc, "f")
         C_ = nm.num_edge_colors
