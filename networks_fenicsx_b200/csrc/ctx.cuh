@@ -64,7 +64,8 @@ struct nxfx_ctx {
   nxfx::DevBuf<int4> slot_uvl;     // [E] {u, v, lm(u), lm(v)} in slot order
   nxfx::DevBuf<int32_t> slot_edge, edge_slot, edge_u, edge_v, bif_ptr, bif_inc;
   // pattern + values
-  nxfx::DevBuf<int32_t> rowptr, colidx;
+  nxfx::DevBuf<int32_t> rowptr, colidx, tile_base;
+  bool pipe_ok = false;  // every row tile fits one pipeline stage
   nxfx::DevBuf<double> vals;
   nxfx::DevBuf<double> cell_rh;  // [nc] R*h per cell, written by the assembly kernel
   // solver workspace

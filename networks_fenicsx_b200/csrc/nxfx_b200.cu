@@ -91,8 +91,18 @@ int build_vertices(nxfx_ctx* ctx) {
 }
 
 // ---- solver building blocks ------------------------------------------------------------------
+constexpr size_t kPipeSmem = kStages * sizeof(SpmvStage) + kStages * sizeof(uint64_t);
+constexpr int kPipeBlocksPerSM = 3;
+
 int do_spmv(nxfx_ctx* ctx, const double* x, double* y) {
   const int ntiles = (int)cdiv(ctx->ndofs, kTileRows);
+  if (ctx->pipe_ok) {
+    const int grid = std::min(ntiles, ctx->sm_count * kPipeBlocksPerSM);
+    NXFX_LAUNCH(ctx, spmv_pipe_kernel<0>, grid, kTileRows, kPipeSmem, (int)ctx->ndofs, ntiles,
+                ctx->rowptr.p, ctx->colidx.p, ctx->vals.p, ctx->tile_base.p, x, y, nullptr, nullptr,
+                nullptr, nullptr);
+    return NXFX_OK;
+  }
   NXFX_LAUNCH(ctx, spmv_kernel<0>, ntiles, kTileRows, 0, (int)ctx->ndofs, ntiles, ctx->rowptr.p,
               ctx->colidx.p, ctx->vals.p, x, y, nullptr, nullptr, nullptr, nullptr);
   return NXFX_OK;
@@ -100,6 +110,13 @@ int do_spmv(nxfx_ctx* ctx, const double* x, double* y) {
 
 int do_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, double* norm2_d) {
   const int ntiles = (int)cdiv(ctx->ndofs, kTileRows);
+  if (ctx->pipe_ok) {
+    const int grid = std::min(ntiles, ctx->sm_count * kPipeBlocksPerSM);
+    NXFX_LAUNCH(ctx, spmv_pipe_kernel<1>, grid, kTileRows, kPipeSmem, (int)ctx->ndofs, ntiles,
+                ctx->rowptr.p, ctx->colidx.p, ctx->vals.p, ctx->tile_base.p, x, r, b, ctx->scal.p,
+                ctx->ticket.p, norm2_d);
+    return NXFX_OK;
+  }
   const int grid = std::min(ntiles, kMaxPartials);
   NXFX_LAUNCH(ctx, spmv_kernel<1>, grid, kTileRows, 0, (int)ctx->ndofs, ntiles, ctx->rowptr.p,
               ctx->colidx.p, ctx->vals.p, x, r, b, ctx->scal.p, ctx->ticket.p, norm2_d);
@@ -539,7 +556,8 @@ int nxfx_symbolic(nxfx_ctx* ctx) {
   Net g = make_net(ctx);
   DevBuf<int32_t> len;
   NXFX_CUDA(ctx, len.alloc((size_t)n + 1));
-  NXFX_CUDA(ctx, ctx->rowptr.alloc((size_t)n + 1));
+  NXFX_CUDA(ctx, ctx->rowptr.alloc((size_t)n + 1 + 8));  // +8: bulk copies round sizes up to 16 B
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->rowptr.p, 0, ((size_t)n + 9) * sizeof(int32_t), ctx->stream));
   NXFX_LAUNCH(ctx, row_len_kernel, (int)cdiv(n + 1, kThreads), kThreads, 0, g, len.p);
   size_t tmp_bytes = 0;
   NXFX_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len.p, ctx->rowptr.p, n + 1, ctx->stream));
@@ -552,11 +570,26 @@ int nxfx_symbolic(nxfx_ctx* ctx) {
   NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   NXFX_REQUIRE(ctx, nnz > 0, "pattern overflow (nnz does not fit int32)");
   ctx->nnz = nnz;
-  NXFX_CUDA(ctx, ctx->colidx.alloc((size_t)nnz));
-  NXFX_CUDA(ctx, ctx->vals.alloc((size_t)nnz));
-  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->vals.p, 0, (size_t)nnz * sizeof(double), ctx->stream));
+  NXFX_CUDA(ctx, ctx->colidx.alloc((size_t)nnz + 8));
+  NXFX_CUDA(ctx, ctx->vals.alloc((size_t)nnz + 8));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->colidx.p, 0, ((size_t)nnz + 8) * sizeof(int32_t), ctx->stream));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->vals.p, 0, ((size_t)nnz + 8) * sizeof(double), ctx->stream));
   NXFX_LAUNCH(ctx, fill_cols_kernel, (int)cdiv(n, kThreads), kThreads, 0, g, ctx->rowptr.p, ctx->colidx.p);
+  // row tiles of the pipelined SpMV
+  const int ntiles = (int)cdiv(n, kTileRows);
+  NXFX_CUDA(ctx, ctx->tile_base.alloc((size_t)ntiles + 2));
+  int32_t* max_tile = reinterpret_cast<int32_t*>(ctx->ticket.p);  // borrowed, reset below
+  NXFX_LAUNCH(ctx, tile_base_kernel, (int)cdiv(ntiles + 1, kThreads), kThreads, 0, n, ntiles, ctx->rowptr.p,
+              ctx->tile_base.p, max_tile);
+  int32_t max_tile_h = 0;
+  NXFX_CUDA(ctx, cudaMemcpyAsync(&max_tile_h, max_tile, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned int), ctx->stream));
   NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->pipe_ok = max_tile_h + 8 <= kPipeCap;
+  if (ctx->pipe_ok) {
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(spmv_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(spmv_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+  }
   ctx->has_pattern = true;
   ctx->assembled = false;
   return NXFX_OK;

@@ -127,6 +127,162 @@ spmv_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
   }
 }
 
+// ---- pipelined SpMV (TMA bulk copies + mbarrier) -----------------------------------------------
+// Persistent blocks walk over row tiles; thread 0 keeps kStages-1 tiles in flight with
+// cp.async.bulk (the TMA engine, SASS UBLKCP): the tile's values, column indices and row pointers
+// land in a shared-memory stage and signal an mbarrier with their byte count.  The other threads
+// only gather x, multiply in place and reduce rows, so HBM streaming never waits for the gather /
+// reduce phases of the same block.
+constexpr int kPipeCap = 1792;  // entries per stage = 7 * kTileRows
+constexpr int kStages = 3;
+
+struct alignas(128) SpmvStage {
+  double vals[kPipeCap];
+  int cols[kPipeCap];
+  int rows[kTileRows + 8];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+
+// tile_base[t] = rowptr[t * kTileRows], tile_base[ntiles] = nnz
+__global__ void __launch_bounds__(kThreads)
+tile_base_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr, int32_t* __restrict__ tile_base,
+                 int32_t* __restrict__ max_tile_nnz) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > ntiles) return;
+  const int r = min(t * kTileRows, n);
+  const int b = rowptr[r];
+  tile_base[t] = b;
+  if (t < ntiles) atomicMax(max_tile_nnz, rowptr[min(r + kTileRows, n)] - b);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTileRows)
+spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
+                 const int32_t* __restrict__ colidx, const double* __restrict__ vals,
+                 const int32_t* __restrict__ tile_base, const double* __restrict__ x,
+                 double* __restrict__ y, const double* __restrict__ b, double* partial,
+                 unsigned int* ticket, double* norm2_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SpmvStage* st = reinterpret_cast<SpmvStage*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(SpmvStage));
+  __shared__ double red[kTileRows / 32];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int tile, int s) {
+    const int r0 = tile * kTileRows;
+    const int nr = min(kTileRows, n - r0);
+    const int sb = tile_base[tile], se = tile_base[tile + 1];
+    const int s4 = sb & ~3;
+    const int cnt4 = ((se + 3) & ~3) - s4;
+    const uint32_t rbytes = (uint32_t)(((nr + 1) * 4 + 15) & ~15);
+    mbar_expect_tx(full + s, (uint32_t)cnt4 * 12u + rbytes);
+    if (cnt4 > 0) {
+      bulk_g2s(st[s].vals, vals + s4, (uint32_t)cnt4 * 8u, full + s);
+      bulk_g2s(st[s].cols, colidx + s4, (uint32_t)cnt4 * 4u, full + s);
+    }
+    bulk_g2s(st[s].rows, rowptr + r0, rbytes, full + s);
+  };
+  if (tid == 0) {
+    for (int k = 0; k < kStages - 1; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      if (tile < ntiles) issue(tile, k);
+    }
+  }
+  double nrm = 0.0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int s = it % kStages;
+    if (tid == 0) {
+      const int pre = tile + (kStages - 1) * gridDim.x;
+      if (pre < ntiles) {
+        // the stage being refilled was multiplied in place by generic-proxy stores
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(pre, (it + kStages - 1) % kStages);
+      }
+    }
+    const int r0 = tile * kTileRows;
+    const int nr = min(kTileRows, n - r0);
+    double bi = 0.0;
+    if (MODE == 1 && tid < nr) bi = b[r0 + tid];
+    mbar_wait(full + s, (uint32_t)((it / kStages) & 1));
+    SpmvStage& S = st[s];
+    const int base = S.rows[0];
+    const int off = base & 3;
+    const int tnnz = S.rows[nr] - base;
+    constexpr int kPer = kPipeCap / kTileRows;
+    int c[kPer];
+    double xv[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int idx = tid + k * kTileRows;
+      if (idx < tnnz) c[k] = S.cols[off + idx];
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int idx = tid + k * kTileRows;
+      if (idx < tnnz) xv[k] = x[c[k]];
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int idx = tid + k * kTileRows;
+      if (idx < tnnz) S.vals[off + idx] = __dmul_rn(S.vals[off + idx], xv[k]);
+    }
+    __syncthreads();
+    if (tid < nr) {
+      const int rs = S.rows[tid] - base + off, re = S.rows[tid + 1] - base + off;
+      double acc = 0.0;
+      for (int k = rs; k < re; ++k) acc = __dadd_rn(acc, S.vals[k]);
+      if (MODE == 0) {
+        y[r0 + tid] = acc;
+      } else {
+        const double r = __dsub_rn(bi, acc);
+        y[r0 + tid] = r;
+        nrm += r * r;
+      }
+    }
+    // order this thread's generic-proxy accesses to the stage before the TMA refill
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
+  if (MODE == 1) {
+    double mine[1] = {block_sum<kTileRows>(nrm, red)};
+    finish_partials<kTileRows, 1>(mine, partial, gridDim.x, ticket, norm2_out, red);
+  }
+}
+
 // ---- vector kernels --------------------------------------------------------------------------
 // out[k] = <a_k, w>, k < K, a_k = A + k*stride (one pass over w)
 template <int K>
