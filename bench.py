@@ -215,8 +215,8 @@ def run_gpu(args):
     bytes_spmv = 12 * nnz + 4 * (n_dofs + 1) + 16 * n_dofs
     bdev = solver.b.duplicate()
     t_asm = time_kernel(
-        dev, lambda: dev.call("nxfx_assemble", asm._pbc_d.c_ptr, None, C.c_double(1.0), None, C.c_double(0.0), 1, 1, 0, bdev.d.c_ptr), reps)
-    bytes_asm = 24 * nv + 8 * nnz + 8 * n_dofs + 8 * n_bnd
+        dev, lambda: dev.call("nxfx_assemble", None, C.c_double(1.0), None, C.c_double(0.0), 1, 1, 0, bdev.d.c_ptr), reps)
+    bytes_asm = 24 * nv + 8 * nnz + 8 * n_dofs + 8 * n_bnd  # coords + values + rhs + p_bc
     t_pcs = time_kernel(dev, lambda: dev.call("nxfx_pc_setup"), reps)
     t_pc = time_kernel(dev, lambda: dev.call("nxfx_pc_apply", solver.b.d.c_ptr, yv.d.c_ptr), reps)
     gbs_spmv = bytes_spmv / (t_spmv * 1e-3) / 1e9

@@ -80,8 +80,10 @@ int nxfx_timer_stop(nxfx_ctx* ctx, double* elapsed_ms); /* synchronises */
  *   bif_ptr_h [n_bif+1], bif_inc_h [I]  incidences of each bifurcation, sorted by flux slot:
  *                               entry = 2*edge + 1 for an in-edge (edge ends at the node),
  *                               2*edge for an out-edge.
- * Builds on the device: vertex coordinates x[n_vertices][3] (graph nodes first, then the N-1
- * interior points of every edge, start*(1-w)+end*w, bit-identical to the reference formula).     */
+ * Builds on the device: vertex records x[n_vertices][4] = {x, y, z, p_bc} (graph nodes first, then
+ * the N-1 interior points of every edge, start*(1-w)+end*w, bit-identical to the reference
+ * formula); one 32-byte record per vertex so that a cell's geometry and boundary data arrive in
+ * one sector each.                                                                                 */
 int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gdim,
                      int32_t cells_per_edge, const double* node_pos_h, const int32_t* edge_u_h,
                      const int32_t* edge_v_h, const int32_t* edge_slot_h, const int32_t* node_lm_h,
@@ -90,7 +92,7 @@ int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gd
 int nxfx_update_node_positions(nxfx_ctx* ctx, const double* node_pos_h);
 int nxfx_get_sizes(const nxfx_ctx* ctx, int64_t* n_vertices, int64_t* n_cells, int64_t* n_dofs,
                    int64_t* nnz);
-int nxfx_mesh_geometry_device(nxfx_ctx* ctx, const double** x_d); /* [n_vertices][3] */
+int nxfx_mesh_geometry_device(nxfx_ctx* ctx, const double** x_d); /* [n_vertices][4]: x, y, z, p_bc */
 
 /* ---- (2) symbolic phase ------------------------------------------------------------------- *
  * Replaces dolfinx.fem.petsc.create_matrix (sparsity pattern + preallocation): solver.py:43,
@@ -103,7 +105,8 @@ int nxfx_csr_device(nxfx_ctx* ctx, const int32_t** rowptr_d, const int32_t** col
 /* ---- (3) numeric assembly ----------------------------------------------------------------- *
  * Replaces fem.petsc.assemble_matrix + A.assemble() + assemble_vector + ghost update:
  * assembly.py:352-367 (forms: assembly.py:253-277).
- *   pbc_vertex_d [n_vertices]   p_bc interpolated into P1 on the parent mesh (assembly.py:225-234)
+ *   nxfx_set_boundary_pressure  p_bc interpolated into P1 on the parent mesh (assembly.py:225-234),
+ *                               pbc_vertex_d [n_vertices]; stored in the vertex records
  *   R_cell_d / f_cell_d [n_cells] per-cell coefficients, or NULL to use R_const / f_const
  *                               (defaults R=1, f=0: assembly.py:201-205)
  *   lhs / rhs                   assemble_lhs / assemble_rhs flags (assembly.py:333-334)
@@ -111,9 +114,9 @@ int nxfx_csr_device(nxfx_ctx* ctx, const int32_t** rowptr_d, const int32_t** col
  *                               1: add to the existing entries (PETSc ADD_VALUES semantics)
  *   b_d [n_dofs]                right-hand side (written when rhs != 0)
  * Matrix values go to the ctx-owned CSR value array (nxfx_csr_device).                            */
-int nxfx_assemble(nxfx_ctx* ctx, const double* pbc_vertex_d, const double* R_cell_d, double R_const,
-                  const double* f_cell_d, double f_const, int lhs, int rhs, int accumulate,
-                  double* b_d);
+int nxfx_set_boundary_pressure(nxfx_ctx* ctx, const double* pbc_vertex_d);
+int nxfx_assemble(nxfx_ctx* ctx, const double* R_cell_d, double R_const, const double* f_cell_d,
+                  double f_const, int lhs, int rhs, int accumulate, double* b_d);
 
 /* ---- (4) solve ---------------------------------------------------------------------------- *
  * Replaces KSP/PC/MUMPS: solver.py:41,51,58-73,127.                                              */

@@ -78,10 +78,11 @@ SIGNATURES = {
     "nxfx_csr_device": (
         C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     ),
+    "nxfx_set_boundary_pressure": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nxfx_assemble": (
         C.c_int,
-        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_int,
-         C.c_int, C.c_void_p],
+        [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int,
+         C.c_void_p],
     ),
     "nxfx_set_tree_schedule": (
         C.c_int,

@@ -172,7 +172,9 @@ class HydraulicNetworkAssembler:
         self._pbc_host = pbc
         if self._pbc_d is None or self._pbc_d.n != pbc.size:
             self._pbc_d = dev.empty(pbc.size)
-        self._pbc_d.upload(pbc)
+        self._pbc_d.upload(pbc, sync=False)
+        dev.call("nxfx_set_boundary_pressure", self._pbc_d.c_ptr)  # into the vertex records
+        dev.sync()
         self._R = self._coefficient(R, 1.0, nc, "R")
         self._f = self._coefficient(f, 0.0, nc, "f")
         C_ = nm.num_edge_colors
@@ -307,7 +309,7 @@ class HydraulicNetworkAssembler:
         f_d, f_c = self._f
         dev.call(
             "nxfx_assemble",
-            self._pbc_d.c_ptr, R_d.c_ptr if R_d is not None else None, C.c_double(R_c),
+            R_d.c_ptr if R_d is not None else None, C.c_double(R_c),
             f_d.c_ptr if f_d is not None else None, C.c_double(f_c),
             int(bool(assemble_lhs)), int(bool(assemble_rhs)), int(acc), b_ptr,
         )

@@ -42,7 +42,8 @@ struct TreeSchedule {
   DevBuf<int32_t> t_of_bif, t_parent, t_pedge, t_cptr, t_cidx, chunk_lptr, lvl_ptr, chord_edge;
   std::vector<int32_t> chunk_lptr_h, lvl_ptr_h;
   // numeric
-  DevBuf<double> diag0, d, gd, r, lam;  // schedule order
+  DevBuf<double> diag0, tg, d, gd, r, lam;  // schedule order
+  bool fast_ok = false;                       // every chunk fits the shared-memory sweep kernel
 };
 
 }  // namespace nxfx
@@ -56,10 +57,10 @@ struct nxfx_ctx {
   int sm_count = 148;
 
   // network
-  bool has_network = false, has_pattern = false, assembled = false, pc_ready = false;
+  bool has_network = false, has_pattern = false, has_pbc = false, assembled = false, pc_ready = false;
   int32_t n_nodes = 0, E = 0, gdim = 0, N = 0, n_bif = 0, n_inc = 0;
   int64_t nv = 0, nc = 0, nq = 0, poff = 0, loff = 0, ndofs = 0, nnz = 0;
-  nxfx::DevBuf<double> x;          // [nv][3] vertex coordinates (graph nodes first)
+  nxfx::DevBuf<double> x;          // [nv][4] vertex records {x, y, z, p_bc} (graph nodes first)
   nxfx::DevBuf<double> pos_stage;  // [n_nodes*gdim] upload staging
   nxfx::DevBuf<int4> slot_uvl;     // [E] {u, v, lm(u), lm(v)} in slot order
   nxfx::DevBuf<int32_t> slot_edge, edge_slot, edge_u, edge_v, bif_ptr, bif_inc;
@@ -73,7 +74,7 @@ struct nxfx_ctx {
   nxfx::DevBuf<double> edge_g, edge_c, edge_fn;  // [E] conductance, condensed rhs, F_N
   nxfx::DevBuf<double> work;                     // krylov vectors
   nxfx::DevBuf<double> scal;                     // device scalars / partials
-  nxfx::DevBuf<unsigned int> ticket;
+  nxfx::DevBuf<unsigned int> ticket;  // [0] reductions, [1] tree sweeps
   double* scal_h = nullptr;  // pinned mirror
   // e2e staging
   nxfx::DevBuf<double> e2e_pbc, e2e_b, e2e_x;

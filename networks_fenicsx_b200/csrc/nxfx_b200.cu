@@ -33,7 +33,7 @@ Net make_net(const nxfx_ctx* c) {
   g.edge_slot = c->edge_slot.p;
   g.bif_ptr = c->bif_ptr.p;
   g.bif_inc = c->bif_inc.p;
-  g.x = c->x.p;
+  g.x2 = reinterpret_cast<const double2*>(c->x.p);
   return g;
 }
 
@@ -48,6 +48,7 @@ TreeDev make_tree(nxfx_ctx* c) {
   t.chunk_lptr = s.chunk_lptr.p;
   t.lvl_ptr = s.lvl_ptr.p;
   t.diag0 = s.diag0.p;
+  t.tg = s.tg.p;
   t.d = s.d.p;
   t.gd = s.gd.p;
   t.r = s.r.p;
@@ -70,8 +71,8 @@ int ensure_scal(nxfx_ctx* ctx) {
   if (ctx->scal.p) return NXFX_OK;
   NXFX_CUDA(ctx, ctx->scal.alloc(kScalPartials + kScalSlots));
   NXFX_CUDA(ctx, cudaMemsetAsync(ctx->scal.p, 0, (kScalPartials + kScalSlots) * sizeof(double), ctx->stream));
-  NXFX_CUDA(ctx, ctx->ticket.alloc(1));
-  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned int), ctx->stream));
+  NXFX_CUDA(ctx, ctx->ticket.alloc(2));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->ticket.p, 0, 2 * sizeof(unsigned int), ctx->stream));
   NXFX_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->scal_h), kScalSlots * sizeof(double), cudaHostAllocDefault));
   return NXFX_OK;
 }
@@ -184,6 +185,16 @@ int tree_pass(nxfx_ctx* ctx, bool factor) {
   auto& s = ctx->tree;
   TreeDev t = make_tree(ctx);
   const int nb = s.n_chunks - 1;  // bottom chunks; the last chunk is the top of the forest
+  if (s.fast_ok) {
+    const int grid = std::max(nb, 1);
+    if (factor) {
+      NXFX_LAUNCH(ctx, tree_fused_kernel<kTreeFactor>, grid, 1024, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1);
+    } else {
+      NXFX_LAUNCH(ctx, tree_fused_kernel<kTreeUp>, grid, 1024, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1);
+      if (nb > 0) NXFX_LAUNCH(ctx, tree_fused_kernel<kTreeDown>, nb, 1024, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1);
+    }
+    return NXFX_OK;
+  }
   if (factor) {
     if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<0>, nb, 1024, 0, t, ctx->edge_g.p, 0);
     NXFX_LAUNCH(ctx, tree_sweep_kernel<0>, 1, 1024, 0, t, ctx->edge_g.p, nb);
@@ -498,7 +509,7 @@ int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gd
   for (int32_t k = 0; k < n_inc; ++k)
     if ((bif_inc[k] >> 1) < 0 || (bif_inc[k] >> 1) >= E)
       return fail(ctx, NXFX_ERR_INVALID, "bif_inc[%d] out of range", k);
-  ctx->has_network = ctx->has_pattern = ctx->assembled = ctx->pc_ready = false;
+  ctx->has_network = ctx->has_pattern = ctx->has_pbc = ctx->assembled = ctx->pc_ready = false;
   ctx->tree.set = false;
   ctx->n_nodes = n_nodes; ctx->E = n_edges; ctx->gdim = gdim; ctx->N = N; ctx->n_bif = n_bif;
   ctx->n_inc = n_inc; ctx->nv = nv; ctx->nc = nc; ctx->nq = nq; ctx->poff = nq; ctx->loff = nq + nc;
@@ -512,7 +523,8 @@ int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gd
   if ((rc = upload(ctx, ctx->slot_uvl, uvl.data(), (size_t)E))) return rc;
   if ((rc = upload(ctx, ctx->bif_ptr, bif_ptr, (size_t)n_bif + 1))) return rc;
   if ((rc = upload(ctx, ctx->bif_inc, bif_inc, (size_t)n_inc))) return rc;
-  NXFX_CUDA(ctx, ctx->x.alloc((size_t)nv * 3));
+  NXFX_CUDA(ctx, ctx->x.alloc((size_t)nv * 4));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->x.p, 0, (size_t)nv * 4 * sizeof(double), ctx->stream));
   NXFX_CUDA(ctx, ctx->cell_rh.alloc((size_t)nc));
   NXFX_CUDA(ctx, ctx->edge_g.alloc((size_t)E));
   NXFX_CUDA(ctx, ctx->edge_c.alloc((size_t)E));
@@ -605,15 +617,23 @@ int nxfx_csr_device(nxfx_ctx* ctx, const int32_t** rowptr, const int32_t** colid
 }
 
 // ---- (3) numeric ---------------------------------------------------------------------------------
-int nxfx_assemble(nxfx_ctx* ctx, const double* pbc, const double* R_cell, double R_const,
-                  const double* f_cell, double f_const, int lhs, int rhs, int accumulate, double* b) {
+int nxfx_set_boundary_pressure(nxfx_ctx* ctx, const double* pbc) {
+  if (!ctx || !pbc) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_network, "no network");
+  NXFX_LAUNCH(ctx, set_pbc_kernel, (int)cdiv(ctx->nv, kThreads), kThreads, 0, ctx->nv, pbc, ctx->x.p);
+  ctx->has_pbc = true;
+  return NXFX_OK;
+}
+
+int nxfx_assemble(nxfx_ctx* ctx, const double* R_cell, double R_const, const double* f_cell,
+                  double f_const, int lhs, int rhs, int accumulate, double* b) {
   if (!ctx) return NXFX_ERR_INVALID;
   NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
-  NXFX_REQUIRE(ctx, !rhs || (b && pbc), "rhs requested without b / p_bc");
+  NXFX_REQUIRE(ctx, !rhs || (b && ctx->has_pbc), "rhs requested without b / boundary pressure");
   if (!lhs && !rhs) return NXFX_OK;
   Net g = make_net(ctx);
   Coef c;
-  c.pbc = pbc; c.R_cell = R_cell; c.f_cell = f_cell; c.R_const = R_const; c.f_const = f_const;
+  c.R_cell = R_cell; c.f_cell = f_cell; c.R_const = R_const; c.f_const = f_const;
   c.cell_rh = ctx->cell_rh.p;
   const int grid = (int)cdiv(ctx->ndofs, kTileRows);
   if (accumulate)
@@ -652,6 +672,18 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
   if ((rc = upload(ctx, s.lvl_ptr, lvl_ptr, (size_t)n_lvl_ptr))) return rc;
   if ((rc = upload(ctx, s.chord_edge, chord_edge, (size_t)std::max(0, n_chords)))) return rc;
   s.n_chunks = n_chunks; s.n_lvl_ptr = n_lvl_ptr; s.n_chords = n_chords;
+  // shared-memory sweeps need every chunk (nodes, levels) to fit the on-chip tables
+  s.fast_ok = true;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int l0 = chunk_lptr[c], l1 = chunk_lptr[c + 1];
+    if (l1 - l0 > kLevelCap || lvl_ptr[l1] - lvl_ptr[l0] > kChunkCap) s.fast_ok = false;
+  }
+  if (s.fast_ok) {
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_fused_kernel<kTreeFactor>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_fused_kernel<kTreeUp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_fused_kernel<kTreeDown>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
+  }
+  NXFX_CUDA(ctx, s.tg.alloc(nb));
   NXFX_CUDA(ctx, s.diag0.alloc(nb));
   NXFX_CUDA(ctx, s.d.alloc(nb));
   NXFX_CUDA(ctx, s.gd.alloc(nb));
@@ -724,7 +756,8 @@ int nxfx_assemble_solve_host(nxfx_ctx* ctx, const double* node_pos, const double
   int rc;
   if ((rc = nxfx_update_node_positions(ctx, node_pos))) return rc;
   NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->e2e_pbc.p, pbc_vertex, (size_t)ctx->nv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = nxfx_assemble(ctx, ctx->e2e_pbc.p, nullptr, R_const, nullptr, f_const, 1, 1, 0, ctx->e2e_b.p))) return rc;
+  if ((rc = nxfx_set_boundary_pressure(ctx, ctx->e2e_pbc.p))) return rc;
+  if ((rc = nxfx_assemble(ctx, nullptr, R_const, nullptr, f_const, 1, 1, 0, ctx->e2e_b.p))) return rc;
   if ((rc = nxfx_solve(ctx, ctx->e2e_b.p, ctx->e2e_x.p, opts, info))) return rc;
   NXFX_CUDA(ctx, cudaMemcpyAsync(x_h, ctx->e2e_x.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

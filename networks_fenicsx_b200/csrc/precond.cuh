@@ -29,6 +29,7 @@ struct TreeDev {
   const int32_t* __restrict__ chunk_lptr;
   const int32_t* __restrict__ lvl_ptr;
   double* diag0;
+  double* tg;  // conductance of the link to the parent (0 for roots)
   double* d;
   double* gd;
   double* r;
@@ -51,7 +52,10 @@ bif_diag_kernel(Net g, TreeDev t, const double* __restrict__ edge_g) {
   if (i >= g.n_bif) return;
   double s = 0.0;
   for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) s += edge_g[g.bif_inc[k] >> 1];
-  t.diag0[t.t_of_bif[i]] = s;
+  const int n = t.t_of_bif[i];
+  t.diag0[n] = s;
+  const int pe = t.t_pedge[n];
+  t.tg[n] = pe >= 0 ? edge_g[pe] : 0.0;
 }
 
 // MODE 0: numeric factorisation  d_t = diag0_t - sum_c g_c^2/d_c ; gd_t = g_t/d_t
@@ -102,6 +106,132 @@ tree_sweep_kernel(TreeDev t, const double* __restrict__ edge_g, int chunk0) {
       __syncthreads();
     }
   }
+}
+
+// ---- shared-memory tree sweeps ------------------------------------------------------------------
+// One thread block per bottom chunk: the chunk's node data, child lists and level table are staged
+// in shared memory once, the level loop then runs on-chip (a level costs a __syncthreads, not an
+// HBM/L2 round trip).  The block that finishes last (atomic ticket) also eliminates the top chunk
+// -- and for the solve runs its back-substitution -- so a sweep is ONE launch; the bottom chunks'
+// back-substitution is a second launch.
+constexpr int kChunkCap = 2048;  // nodes per chunk held in shared memory
+constexpr int kLevelCap = 64;    // levels per chunk held in shared memory
+
+struct TreeSmem {
+  double a[kChunkCap];  // F: d      U: r      D: lam
+  double b[kChunkCap];  // F: tg     U: d(top) D: d
+  double c[kChunkCap];  // F: gd     U: gd     D: gd
+  int cptr[kChunkCap + 1];
+  int cidx[kChunkCap];
+  int lvl[kLevelCap + 1];
+  int last;
+};
+
+enum { kTreeFactor = 0, kTreeUp = 1, kTreeDown = 2 };
+
+template <int MODE>
+__device__ __forceinline__ void tree_chunk(const TreeDev& t, TreeSmem& S, int chunk, bool top) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int L0 = t.chunk_lptr[chunk], L1 = t.chunk_lptr[chunk + 1];
+  const int nl = L1 - L0;
+  for (int i = tid; i <= nl; i += nth) S.lvl[i] = t.lvl_ptr[L0 + i];
+  __syncthreads();
+  const int b0 = S.lvl[0], b1 = S.lvl[nl], nn = b1 - b0;
+  if (MODE != kTreeDown) {
+    const int cb = t.t_cptr[b0], ce = t.t_cptr[b1];
+    for (int i = tid; i <= nn; i += nth) S.cptr[i] = t.t_cptr[b0 + i] - cb;
+    for (int i = tid; i < ce - cb; i += nth) S.cidx[i] = t.t_cidx[cb + i];
+  }
+  if (MODE == kTreeFactor) {
+    for (int i = tid; i < nn; i += nth) { S.a[i] = t.diag0[b0 + i]; S.b[i] = t.tg[b0 + i]; }
+  } else if (MODE == kTreeUp) {
+    for (int i = tid; i < nn; i += nth) {
+      S.a[i] = t.r[b0 + i];
+      S.c[i] = t.gd[b0 + i];
+      if (top) S.b[i] = t.d[b0 + i];
+    }
+  } else {
+    for (int i = tid; i < nn; i += nth) {
+      S.a[i] = t.r[b0 + i];
+      S.b[i] = t.d[b0 + i];
+      S.c[i] = t.gd[b0 + i];
+    }
+  }
+  __syncthreads();
+  if (MODE != kTreeDown) {
+    if (top) {
+      // children that live in bottom chunks were finished by other blocks of this launch:
+      // read them through L2 (__ldcg), fold them in before the on-chip level loop
+      for (int i = tid; i < nn; i += nth) {
+        double acc = S.a[i];
+        for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+          const int c = S.cidx[k];
+          if (c < b0) {
+            if (MODE == kTreeFactor) acc -= t.tg[c] * __ldcg(t.gd + c);
+            else acc += t.gd[c] * __ldcg(t.r + c);
+          }
+        }
+        S.a[i] = acc;
+      }
+      __syncthreads();
+    }
+    for (int L = nl - 1; L >= 0; --L) {
+      for (int n = S.lvl[L] + tid; n < S.lvl[L + 1]; n += nth) {
+        const int i = n - b0;
+        double acc = S.a[i];
+        for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+          const int c = S.cidx[k] - b0;
+          if (c >= 0) {
+            if (MODE == kTreeFactor) acc -= S.b[c] * S.c[c];
+            else acc += S.c[c] * S.a[c];
+          }
+        }
+        S.a[i] = acc;
+        if (MODE == kTreeFactor) S.c[i] = S.b[i] / acc;
+      }
+      __syncthreads();
+    }
+    if (MODE == kTreeFactor) {
+      for (int i = tid; i < nn; i += nth) { t.d[b0 + i] = S.a[i]; t.gd[b0 + i] = S.c[i]; }
+    } else if (!top) {
+      for (int i = tid; i < nn; i += nth) t.r[b0 + i] = S.a[i];
+    }
+  }
+  if (MODE == kTreeDown || (MODE == kTreeUp && top)) {
+    // back-substitution, shallowest level first: lam = r/d + gd * lam(parent)
+    for (int L = 0; L < nl; ++L) {
+      for (int n = S.lvl[L] + tid; n < S.lvl[L + 1]; n += nth) {
+        const int i = n - b0;
+        const int p = t.t_parent[n];
+        double v = S.a[i] / S.b[i];
+        if (p >= b0 && p < b1) v += S.c[i] * S.a[p - b0];
+        else if (p >= 0) v += S.c[i] * t.lam[p];
+        S.a[i] = v;
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < nn; i += nth) t.lam[b0 + i] = S.a[i];
+  }
+}
+
+// grid = max(n_bottom, 1); MODE kTreeFactor / kTreeUp run the top chunk in the last block.
+template <int MODE>
+__global__ void __launch_bounds__(1024)
+tree_fused_kernel(TreeDev t, int n_bottom, unsigned int* ticket) {
+  extern __shared__ __align__(16) unsigned char tree_smem_raw[];
+  TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
+  if (n_bottom > 0) tree_chunk<MODE>(t, S, blockIdx.x, false);
+  if (MODE == kTreeDown) return;
+  if (n_bottom > 0) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) S.last = (atomicAdd(ticket, 1u) == (unsigned int)n_bottom - 1);
+    __syncthreads();
+    if (!S.last) return;
+    __threadfence();
+  }
+  tree_chunk<MODE>(t, S, n_bottom, true);
+  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // Edge condensation: c_e = sum r_q - w.F,  F_N = sum r_p

@@ -470,14 +470,14 @@ class NetworkMesh:
         return self._dev
 
     def geometry_device(self) -> DeviceArray:
-        """Borrowed view of the device vertex coordinates, shape (n_vertices*3,)."""
+        """Borrowed view of the device vertex records {x, y, z, p_bc}, shape (n_vertices*4,)."""
         p = C.c_void_p()
         self.device.call("nxfx_mesh_geometry_device", C.byref(p))
-        return DeviceArray(self.device, self._n_vertices * 3, np.float64, ptr=p.value)
+        return DeviceArray(self.device, self._n_vertices * 4, np.float64, ptr=p.value)
 
     def _geometry_x(self) -> npt.NDArray[np.float64]:
         if self._x_host is None:
-            self._x_host = self.geometry_device().download().reshape(-1, 3)
+            self._x_host = np.ascontiguousarray(self.geometry_device().download().reshape(-1, 4)[:, :3])
         return self._x_host
 
     def _cells(self) -> npt.NDArray[np.int64]:
