@@ -123,6 +123,7 @@ struct TreeSmem {
   double c[kChunkCap];  // F: gd     U: gd     D: gd
   int cptr[kChunkCap + 1];
   int cidx[kChunkCap];
+  int par[kChunkCap];
   int lvl[kLevelCap + 1];
   int last;
 };
@@ -148,13 +149,14 @@ __device__ __forceinline__ void tree_chunk(const TreeDev& t, TreeSmem& S, int ch
     for (int i = tid; i < nn; i += nth) {
       S.a[i] = t.r[b0 + i];
       S.c[i] = t.gd[b0 + i];
-      if (top) S.b[i] = t.d[b0 + i];
+      if (top) { S.b[i] = t.d[b0 + i]; S.par[i] = t.t_parent[b0 + i]; }
     }
   } else {
     for (int i = tid; i < nn; i += nth) {
       S.a[i] = t.r[b0 + i];
       S.b[i] = t.d[b0 + i];
       S.c[i] = t.gd[b0 + i];
+      S.par[i] = t.t_parent[b0 + i];
     }
   }
   __syncthreads();
@@ -202,7 +204,7 @@ __device__ __forceinline__ void tree_chunk(const TreeDev& t, TreeSmem& S, int ch
     for (int L = 0; L < nl; ++L) {
       for (int n = S.lvl[L] + tid; n < S.lvl[L + 1]; n += nth) {
         const int i = n - b0;
-        const int p = t.t_parent[n];
+        const int p = S.par[i];
         double v = S.a[i] / S.b[i];
         if (p >= b0 && p < b1) v += S.c[i] * S.a[p - b0];
         else if (p >= 0) v += S.c[i] * t.lam[p];

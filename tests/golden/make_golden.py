@@ -64,8 +64,8 @@ def main():
                 key = f"tree_n{n}_H{H}_W{W}_d{dim}"
                 for k, v in graph_arrays(G).items():
                     data[f"{key}/{k}"] = v
-    for n in (3, 5, 8):
-        G = ref.make_tree(n, n, n)
+    for n in (3, 5, 7):
+        G = ref.make_tree(n, 1, 1)
         for strat in ("smallest_last", "largest_first"):
             data[f"color_tree_n{n}_{strat}"] = reference_coloring(G, strat)
     for N, direction, gamma in ((1, [0, 1, 0], 0.8), (3, [0, 1, 0], 0.8), (5, [0.1, 1, 0], 0.8), (6, [1, 1, 0], 0.5)):

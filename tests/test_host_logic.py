@@ -1,0 +1,286 @@
+"""Host-side logic of the product (no GPU): generators against the reference fixtures, graph
+analysis / dof layout against the oracle's literal restatement, the reference's own structural
+tests on the NetworkMesh duck types, the elimination schedule."""
+
+import pathlib
+
+import networkx as nx
+import numpy as np
+import pytest
+
+import networks_fenicsx_b200 as nxfx
+from networks_fenicsx_b200 import network_generation as ng
+from networks_fenicsx_b200.mesh import _greedy_edge_coloring_arrays, color_graph
+from networks_fenicsx_b200.schedule import build_tree_schedule
+from oracle import reference_port as rp
+from tests import helpers
+
+GOLDEN = np.load(pathlib.Path(__file__).parent / "golden" / "reference_graphs.npz")
+
+
+def graph_arrays(G):
+    pos = np.asarray([G.nodes[v]["pos"] for v in G.nodes()], dtype=float)
+    return pos, np.asarray(list(G.edges()), dtype=np.int64)
+
+
+# ---- generators: bit-for-bit against the reference's make_tree / make_arterial_tree --------------
+def test_make_tree_matches_reference_fixtures():
+    keys = sorted({k.split("/")[0] for k in GOLDEN.files if k.startswith("tree_")})
+    assert len(keys) >= 30
+    for key in keys:
+        _, n, H, W, d = key.split("_")
+        n, H, W, d = int(n[1:]), float(H[1:]), float(W[1:]), int(d[1:])
+        H, W = (int(H) if H == int(H) else H), (int(W) if W == int(W) else W)
+        G = ng.make_tree(n, H, W, d)
+        pos, edges = graph_arrays(G)
+        assert np.array_equal(pos, GOLDEN[key + "/pos"]) and np.array_equal(edges, GOLDEN[key + "/edges"]), key
+        assert list(G.nodes()) == GOLDEN[key + "/nodes"].tolist()
+        A = ng.make_tree(n, H, W, d, as_arrays=True)
+        assert np.array_equal(A.pos, pos) and np.array_equal(A.edges, edges)
+
+
+def test_make_arterial_tree_matches_reference_fixtures():
+    keys = sorted({k.split("/")[0] for k in GOLDEN.files if k.startswith("arterial_")})
+    assert len(keys) == 4
+    for key in keys:
+        parts = key.split("_")
+        N, gam = int(parts[1][1:]), float(parts[2][1:])
+        direction = np.array([float(parts[3][1:])] + [float(x) for x in parts[4:]])
+        G = ng.make_arterial_tree(N=N, direction=direction, gamma=gam)
+        pos, edges = graph_arrays(G)
+        radius = np.asarray([G.edges[e]["radius"] for e in G.edges()])
+        assert np.array_equal(pos, GOLDEN[key + "/pos"]), key
+        assert np.array_equal(edges, GOLDEN[key + "/edges"])
+        assert np.array_equal(radius, GOLDEN[key + "/radius"])
+        A = ng.make_arterial_tree(N=N, direction=direction, gamma=gam, as_arrays=True)
+        assert np.array_equal(A.pos, pos) and np.array_equal(A.edge_attrs["radius"], radius)
+    with pytest.raises(ValueError):
+        ng.make_arterial_tree(3, gamma=1.5)
+
+
+def test_large_tree_generation_is_fast():
+    A = ng.make_tree(18, 18, 18, as_arrays=True)
+    assert A.number_of_edges() == 2**18 - 1 and A.pos.shape == (2**18, 3)
+
+
+# ---- colouring ---------------------------------------------------------------------------------
+def test_color_graph_matches_reference_call_sequence():
+    for n in (3, 5, 7):
+        G = ng.make_tree(n, 1, 1)
+        for strat in ("smallest_last", "largest_first"):
+            nm = nxfx.NetworkMesh(G, N=1, color_strategy=strat)
+            assert nm.edge_colors.tolist() == GOLDEN[f"color_tree_n{n}_{strat}"].tolist()
+    G = ng.make_tree(3, 1, 1)
+    assert color_graph(G, None) == {e: i for i, e in enumerate(G.edges)}
+    nm = nxfx.NetworkMesh(G, N=2, color_strategy=nx.coloring.strategy_largest_first)
+    assert nm.num_edge_colors == 3
+
+
+def test_reversed_edge_keys_do_not_raise():
+    """the reference raises KeyError for edges keyed (v,u) by the line graph."""
+    G = nx.DiGraph()
+    for i in range(4):
+        G.add_node(i, pos=np.array([float(i), 0.0]))
+    for e in [(1, 0), (2, 1), (3, 2)]:
+        G.add_edge(*e)
+    nm = nxfx.NetworkMesh(G, N=2, color_strategy="largest_first")
+    assert nm.num_edge_colors == 2
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_native_greedy_coloring_is_proper(seed):
+    G = helpers.random_tree(300, seed)
+    edges = np.asarray(list(G.edges()), dtype=np.int64)
+    col = _greedy_edge_coloring_arrays(300, edges)
+    deg = np.bincount(edges.ravel())
+    assert col.min() == 0 and col.max() + 1 <= 2 * deg.max() - 1
+    for node in range(300):
+        inc = col[(edges[:, 0] == node) | (edges[:, 1] == node)]
+        assert len(inc) == len(set(inc.tolist()))
+    A = ng.make_tree(12, 1, 1, as_arrays=True)
+    assert _greedy_edge_coloring_arrays(A.number_of_nodes(), A.edges).max() == 2  # 3 colours on a binary tree
+
+
+# ---- NetworkMesh host analysis vs the oracle's literal restatement of mesh.py ----------------------
+CASES = [
+    ("edge_info", helpers.edge_info_graph, None, 10),
+    ("edge_info_col", helpers.edge_info_graph, "largest_first", 3),
+    ("tree5", lambda: ng.make_tree(5, 1, 1), "smallest_last", 4),
+    ("tree3_uncol", lambda: ng.make_tree(3, 2, 1, 2), None, 1),
+    ("line_alt", lambda: helpers.linear_graph(12, ordered=lambda k: k % 2), None, 2),
+    ("random", lambda: helpers.random_tree(80, 3), "smallest_last", 2),
+    ("two_junctions", helpers.double_junction_graph, "largest_first", 5),
+]
+
+
+@pytest.mark.parametrize("name,make,strategy,N", CASES)
+def test_network_mesh_matches_literal_reference_logic(name, make, strategy, N):
+    G = make()
+    nm = nxfx.NetworkMesh(G, N=N, color_strategy=strategy)
+    col = rp.color_graph_literal(G, strategy)
+    info = rp.analyse_graph_literal(G, col)
+    assert nm.num_edge_colors == info.num_edge_colors
+    np.testing.assert_array_equal(nm.bifurcation_values, info.bifurcation_values)
+    np.testing.assert_array_equal(nm.boundary_values, info.boundary_values)
+    for i in range(len(info.bifurcation_values)):
+        np.testing.assert_array_equal(nm.in_edges(i), info.in_color[info.in_offsets[i]:info.in_offsets[i + 1]])
+        np.testing.assert_array_equal(nm.out_edges(i), info.out_color[info.out_offsets[i]:info.out_offsets[i + 1]])
+    tags, im, om = rp.vertex_markers_literal(info)
+    assert (nm.in_marker, nm.out_marker) == (im, om)
+    np.testing.assert_array_equal(nm.boundaries.values, tags)
+    nodes, cells, markers, orient = rp.mesh_arrays_literal(G, N, col)
+    np.testing.assert_array_equal(nm._cells(), cells)
+    np.testing.assert_array_equal(nm.subdomains.values, markers)
+    np.testing.assert_array_equal(nm.orientation.x.array, rp.orientation_net_effect(cells))
+    assert nm.mesh.topology.dim == 1 and nm.mesh.geometry.dim == nodes.shape[1]
+    assert nm.mesh.topology.index_map(1).size_global == cells.shape[0]
+    assert nm.mesh.topology.index_map(0).size_global == nodes.shape[0]
+    # dof layout against the oracle
+    net = rp.OracleNetwork(*rp.graph_to_arrays(G, col), N)
+    np.testing.assert_array_equal(nm.edge_slot * (N + 1), net.fb)
+    asm = nxfx.HydraulicNetworkAssembler(nm)
+    assert asm.block_sizes == net.block_sizes and asm.num_dofs == net.n_dofs
+    # integration entities (assembly.py:28-92)
+    infl, outfl = rp.integration_entities_literal(G, N, col, info)
+    data = dict(asm._integration_data)
+    for c in range(nm.num_edge_colors):
+        np.testing.assert_array_equal(data[asm._in_idx + c], infl[c])
+        np.testing.assert_array_equal(data[asm._out_idx + c], outfl[c])
+    # entity maps / submeshes
+    for c in range(min(nm.num_edge_colors, 4)):
+        cells_c = nm.entity_maps[c].sub_topology_to_topology(np.arange(nm.submeshes[c].topology.index_map(1).size_local))
+        np.testing.assert_array_equal(cells_c, np.flatnonzero(markers == c))
+        np.testing.assert_array_equal(nm.entity_maps[c].sub_topology_to_topology(cells_c, inverse=True), np.arange(cells_c.size))
+    assert nm.lm_mesh.topology.index_map(0).size_global == len(info.bifurcation_values)
+    # incidence table: sorted by slot within a bifurcation, signs = in/out
+    for i, b in enumerate(nm.bifurcation_values):
+        inc = nm._bif_inc[nm._bif_ptr[i]:nm._bif_ptr[i + 1]]
+        e = inc >> 1
+        assert np.all(np.diff(nm.edge_slot[e]) > 0)
+        for code in inc:
+            u, v = nm.graph_edges[code >> 1]
+            assert (v == b) if (code & 1) else (u == b)
+
+
+@pytest.mark.parametrize("N", [10, 50])
+def test_edge_info_reference_test(N):
+    """tests/test_edge_info.py of the reference, verbatim assertions."""
+    network_mesh = nxfx.NetworkMesh(helpers.edge_info_graph(), N=N)
+    assert len(network_mesh.bifurcation_values) == 6
+    np.testing.assert_allclose([1, 2, 3, 4, 5, 7], network_mesh.bifurcation_values)
+    expected = [(1, 1), (1, 1), (1, 1), (2, 1), (2, 1), (1, 3)]
+    for i, (n_in, n_out) in enumerate(expected):
+        assert len(network_mesh.in_edges(i)) == n_in
+        assert len(network_mesh.out_edges(i)) == n_out
+
+
+@pytest.mark.parametrize("gdim", [2, 3])
+@pytest.mark.parametrize("N", [1, 4, 10])
+@pytest.mark.parametrize("n", [2, 5, 7])
+@pytest.mark.parametrize("H", [1, 2])
+def test_make_tree_reference_test(n, H, gdim, N):
+    """tests/test_make_tree.py of the reference, verbatim assertions."""
+    G = ng.make_tree(n=n, H=H, W=1, dim=gdim)
+    network_mesh = nxfx.NetworkMesh(G, N=N)
+    domain = network_mesh.mesh
+    tdim = domain.topology.dim
+    assert tdim == 1
+    assert domain.geometry.dim == gdim
+    num_segments = sum(2**i for i in range(n))
+    assert domain.topology.index_map(tdim).size_global == N * num_segments
+    assert domain.topology.index_map(0).size_global == N + 1 + (num_segments - 1) * N
+
+
+def test_invalid_inputs():
+    G = nx.DiGraph()
+    G.add_node(5, pos=np.zeros(2))
+    G.add_node(0, pos=np.ones(2))
+    G.add_edge(5, 0)
+    with pytest.raises(ValueError):
+        nxfx.NetworkMesh(G, N=1)
+    with pytest.raises(ValueError):
+        nxfx.NetworkMesh(ng.make_tree(2, 1, 1), N=0)
+    nm = nxfx.NetworkMesh(ng.make_tree(2, 1, 1), N=1)
+    with pytest.raises(NotImplementedError):
+        nxfx.HydraulicNetworkAssembler(nm, flux_degree=2, pressure_degree=1)
+    assert nxfx.__version__ is not None  # tests/test_version.py
+
+
+def test_api_surface_matches_reference():
+    """__init__.py:19-25 exports and the public method names of the three classes."""
+    for name in ["HydraulicNetworkAssembler", "NetworkMesh", "post_processing", "Solver", "network_generation"]:
+        assert hasattr(nxfx, name)
+    for name in ["lm_mesh", "lm_map", "comm", "submesh_facet_markers", "mesh", "subdomains", "boundaries", "submeshes",
+                 "entity_maps", "orientation", "bifurcation_values", "boundary_values", "in_edges", "out_edges",
+                 "num_edge_colors", "in_marker", "out_marker"]:
+        assert hasattr(nxfx.NetworkMesh, name), name
+    for name in ["compute_forms", "lm_space", "pressure_space", "flux_spaces", "function_spaces", "network", "assemble",
+                 "bilinear_forms", "bilinear_form", "linear_forms", "linear_form"]:
+        assert hasattr(nxfx.HydraulicNetworkAssembler, name), name
+    for name in ["assembler", "A", "b", "assemble", "ksp", "solve"]:
+        assert hasattr(nxfx.Solver, name), name
+    for name in ["extract_global_flux", "export_functions", "export_submeshes"]:
+        assert hasattr(nxfx.post_processing, name)
+    from networks_fenicsx_b200.common import timed, timing
+
+    @timed("nxfx:test")
+    def f():
+        return 1
+
+    f()
+    assert timing("nxfx:test")[0] == 1
+
+
+# ---- elimination schedule -----------------------------------------------------------------------
+def check_schedule(nm, s, chunk_nodes):
+    n_bif = nm.bifurcation_values.size
+    assert sorted(s.t_of_bif.tolist()) == list(range(n_bif))
+    assert s.lvl_ptr[0] == 0 and s.lvl_ptr[-1] == n_bif and s.chunk_lptr[-1] == s.lvl_ptr.size - 1
+    lm = nm.node_multiplier_index
+    bif_of_t = np.argsort(s.t_of_bif)
+    level_of = np.repeat(np.arange(s.lvl_ptr.size - 1), np.diff(s.lvl_ptr))
+    chunk_of_level = np.repeat(np.arange(s.n_chunks), np.diff(s.chunk_lptr))
+    n_tree_edges = 0
+    for t in range(n_bif):
+        p, e = s.t_parent[t], s.t_pedge[t]
+        assert (p >= 0) == (e >= 0)
+        if p >= 0:
+            n_tree_edges += 1
+            u, v = nm.graph_edges[e]
+            assert {int(lm[u]), int(lm[v])} == {int(bif_of_t[t]), int(bif_of_t[p])}
+            ct, cp = chunk_of_level[level_of[t]], chunk_of_level[level_of[p]]
+            # the parent is in the same chunk at a shallower level, or in the top (last) chunk
+            assert (ct == cp and level_of[p] < level_of[t]) or (cp == s.n_chunks - 1 and ct != cp)
+            assert t in s.t_cidx[s.t_cptr[p]:s.t_cptr[p + 1]]
+    assert s.t_cptr[-1] == n_tree_edges
+    for c in range(s.n_chunks - 1):
+        lo, hi = s.lvl_ptr[s.chunk_lptr[c]], s.lvl_ptr[s.chunk_lptr[c + 1]]
+        assert 0 < hi - lo <= chunk_nodes
+    links = [(u, v) for u, v in nm.graph_edges if lm[u] >= 0 and lm[v] >= 0]
+    assert len(links) == n_tree_edges + s.chord_edge.size
+
+
+@pytest.mark.parametrize("name,make,chunk", [
+    ("tree9", lambda: ng.make_tree(9, 1, 1), 16), ("tree9_big", lambda: ng.make_tree(9, 1, 1), 2048),
+    ("random", lambda: helpers.random_tree(400, 5), 32), ("cyclic", helpers.edge_info_graph, 4),
+    ("line", lambda: helpers.linear_graph(30), 8), ("y", lambda: ng.make_tree(2, 1, 3), 2048),
+])
+def test_tree_schedule(name, make, chunk):
+    nm = nxfx.NetworkMesh(make(), N=1)
+    s = build_tree_schedule(nm.graph_edges, nm.node_multiplier_index, nm.bifurcation_values.size,
+                            root_hint_nodes=nm._boundary_out_nodes, chunk_nodes=chunk)
+    check_schedule(nm, s, chunk)
+    assert s.is_forest == (name != "cyclic")
+    if name == "cyclic":
+        assert s.chord_edge.size == 2  # 7 links among 6 bifurcations, spanning tree has 5
+
+
+def test_single_edge_graph_has_empty_schedule():
+    G = nx.DiGraph()
+    G.add_node(0, pos=np.zeros(3))
+    G.add_node(1, pos=np.ones(3))
+    G.add_edge(0, 1)
+    nm = nxfx.NetworkMesh(G, N=3)
+    assert nm.bifurcation_values.size == 0
+    s = build_tree_schedule(nm.graph_edges, nm.node_multiplier_index, 0)
+    assert s.n_chunks == 0
