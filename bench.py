@@ -100,10 +100,23 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_problem(n, device_index):
+def build_problem(n, device_index, rank=0, world=1):
     import networks_fenicsx_b200 as nxfx
 
     G = nxfx.network_generation.make_tree(n, n, n, as_arrays=True)
+    if world > 1:
+        # weak scaling: a forest of `world` n-generation trees, partitioned by connected component
+        # (zero-cut edge partition): every rank ends up owning exactly one tree
+        from networks_fenicsx_b200 import parallel
+
+        trees = []
+        for k in range(world):
+            t = nxfx.network_generation.ArrayGraph(G.pos.copy(), G.edges)
+            t.pos[:, 0] += 2.0 * n * k
+            trees.append(t)
+        F = parallel.forest(trees)
+        rank_of_edge = parallel.partition_components(F.edges, F.number_of_nodes(), world)
+        G = parallel.local_part(F, rank_of_edge, rank).graph
     nm = nxfx.NetworkMesh(G, N=1, color_strategy="smallest_last", device=device_index)
     asm = nxfx.HydraulicNetworkAssembler(nm, flux_degree=1, pressure_degree=0)
     asm.compute_forms(p_bc_ex=p_bc)
@@ -139,7 +152,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n = args.generations
-    nxfx, nm, asm, solver = build_problem(n, local_rank)
+    nxfx, nm, asm, solver = build_problem(n, local_rank, rank, world)
     dev = nm.device
     n_dofs = asm.num_dofs
     solver.assemble()
