@@ -136,6 +136,8 @@ typedef struct {
   int32_t restart;      /* FGMRES restart length */
   int32_t refine_steps; /* PREONLY: iterative-refinement steps after the first apply */
   int32_t error_if_not_converged;
+  int32_t final_residual; /* PREONLY: also evaluate the true residual of the final iterate */
+  int32_t reserved;
 } nxfx_solve_opts;
 
 #define NXFX_HISTORY_LEN 128

@@ -26,6 +26,8 @@ class SolveOpts(C.Structure):
         ("restart", C.c_int32),
         ("refine_steps", C.c_int32),
         ("error_if_not_converged", C.c_int32),
+        ("final_residual", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

@@ -18,9 +18,38 @@
 
 namespace nxfx {
 
+// Division by a runtime constant d >= 2 without the ~25-instruction integer divide
+// (libdivide's branch-free u32 scheme): q = (((n - t) >> 1) + t) >> shift, t = umulhi(n, magic).
+struct FastDiv {
+  uint32_t magic, shift;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t fl = 31;
+  while (!((d >> fl) & 1u)) --fl;
+  if ((d & (d - 1)) == 0) {
+    f.magic = 0;
+    f.shift = fl == 0 ? 0 : fl - 1;  // d == 1 is never passed by the kernels
+  } else {
+    const uint64_t n = 1ull << (32 + fl);
+    uint64_t m = n / d;
+    const uint64_t rem = n % d;
+    m += m;
+    if (2 * rem >= d) m += 1;
+    f.magic = (uint32_t)(m + 1);
+    f.shift = fl;
+  }
+  return f;
+}
+__device__ __forceinline__ int fastdiv(int n, FastDiv f) {
+  const uint32_t t = __umulhi((uint32_t)n, f.magic);
+  return (int)(((((uint32_t)n - t) >> 1) + t) >> f.shift);
+}
+
 struct Net {
   int32_t n_nodes, E, N, n_bif;
   int32_t nq, poff, loff, ndofs;
+  FastDiv div_np1, div_n;  // divide by N+1 / N (valid when N >= 2)
   const int4* __restrict__ slot_uvl;
   const int32_t* __restrict__ slot_edge;
   const int32_t* __restrict__ edge_slot;
@@ -174,42 +203,46 @@ fill_cols_kernel(Net g, const int32_t* __restrict__ rowptr, int32_t* __restrict_
 // it loads the two vertex records of that cell, evaluates m_a = R_a h_a and hands m_a and the
 // boundary pressure of the cell's end vertex to the next row of the same edge by warp shuffle
 // (the previous cell's contribution to the shared-vertex mass entry), so every cell is evaluated
-// once per warp.  Entries are staged in shared memory at the row's CSR offset and streamed out
-// coalesced.
+// once per warp.  Entries are staged in shared memory at the row's CSR offset (branch-free,
+// predicated stores) and streamed out with 16-byte stores.  N1 = one cell per edge (compile-time
+// fast path of the headline workload); otherwise N >= 2 with magic-number division.
+struct SmemSink {
+  double* sm;
+  __device__ __forceinline__ void operator()(bool on, int idx, double v) const {
+    if (on) sm[idx] = v;
+  }
+};
 template <bool ACC>
-__global__ void __launch_bounds__(kTileRows)
-assemble_rows_kernel(Net g, Coef c, const int32_t* __restrict__ rowptr, double* __restrict__ vals,
-                     double* __restrict__ b, int lhs, int rhs) {
-  __shared__ double sm[kTileCap];
-  const int r0 = blockIdx.x * kTileRows;
-  const int r = r0 + threadIdx.x;
-  const int rend = min(r0 + kTileRows, g.ndofs);
-  const int sbase = rowptr[r0];
-  const int tnnz = rowptr[rend] - sbase;
-  const int lane = threadIdx.x & 31;
-  const int N = g.N;
-  int p = r < g.ndofs ? rowptr[r] - sbase : 0;  // running position inside the tile
-  auto put = [&](double v) {
-    if (p < kTileCap) sm[p] = v;
-    else if (lhs) {
-      if (ACC) vals[(size_t)sbase + p] += v; else vals[(size_t)sbase + p] = v;
+struct GlobalSink {  // tiles larger than the staging buffer (very high degree bifurcations)
+  double* vals;
+  __device__ __forceinline__ void operator()(bool on, int idx, double v) const {
+    if (on) {
+      if (ACC) vals[idx] += v; else vals[idx] = v;
     }
-    ++p;
-  };
+  }
+};
+
+// Everything a row needs from the index tables.
+struct RowDesc {
+  int sbase, tnnz, start;  // tile base / size, row offset inside the tile
+  int a, e;                // flux rows: local vertex, graph edge
+  int4 t;                  // flux rows: {u, v, lm(u), lm(v)}
+  int i0, i1;              // multiplier rows: incidence range
+};
+
+template <bool ACC, bool N1, typename Sink>
+__device__ __forceinline__ void assemble_row(const Net& g, const Coef& c, const RowDesc& d, int r, int p,
+                                             int lane, double* __restrict__ b, int rhs, const Sink& put) {
+  const int N = N1 ? 1 : g.N;
   // ---- flux rows: geometry phase (all lanes take part in the shuffles) ----------------------
   const bool isflux = r < g.nq;
-  int a = 0, e = 0;
-  int4 t = make_int4(0, 0, -1, -1);
+  const int a = d.a, e = d.e;
+  const int4 t = d.t;
   double mR = 0.0, pA = 0.0, pNext = 0.0;
   if (isflux) {
-    const int np1 = N + 1;
-    const int slot = r / np1;
-    a = r - slot * np1;
-    t = g.slot_uvl[slot];
-    e = g.slot_edge[slot];
     if (a < N) {
-      const VertexRec v0 = load_vertex(g.x2, vertex_id(g, e, t.x, t.y, a));
-      const VertexRec v1 = load_vertex(g.x2, vertex_id(g, e, t.x, t.y, a + 1));
+      const VertexRec v0 = load_vertex(g.x2, N1 ? t.x : vertex_id(g, e, t.x, t.y, a));
+      const VertexRec v1 = load_vertex(g.x2, N1 ? t.y : vertex_id(g, e, t.x, t.y, a + 1));
       const double R = c.R_cell ? c.R_cell[(size_t)e * N + a] : c.R_const;
       mR = __dmul_rn(R, seg_length(v0, v1));
       c.cell_rh[(size_t)e * N + a] = mR;
@@ -222,7 +255,7 @@ assemble_rows_kernel(Net g, Coef c, const int32_t* __restrict__ rowptr, double* 
   if (isflux) {
     double mL = 0.0;
     if (a > 0) {
-      if (lane > 0) {  // the previous lane owns cell a-1 of the same edge
+      if (N1 || lane > 0) {  // the previous lane owns cell a-1 of the same edge
         mL = mPrev;
         if (a == N) pA = pPrev;
       } else {  // first lane of the warp: evaluate cell a-1 here
@@ -233,27 +266,27 @@ assemble_rows_kernel(Net g, Coef c, const int32_t* __restrict__ rowptr, double* 
         pA = v1.p;
       }
     }
+    const bool hasL = a > 0, hasR = a < N;
     // mass block (assembly.py:253): R h [[1/3,1/6],[1/6,1/3]] per cell
-    if (a > 0) put(__dmul_rn(mL, kSixth));
-    put(a == 0 ? __dmul_rn(mR, kThird)
-               : (a == N ? __dmul_rn(mL, kThird)
-                         : __dadd_rn(__dmul_rn(mL, kThird), __dmul_rn(mR, kThird))));
-    if (a < N) put(__dmul_rn(mR, kSixth));
+    const double dL = __dmul_rn(mL, kThird), dR = __dmul_rn(mR, kThird);
+    const double diag = hasL ? (hasR ? __dadd_rn(dL, dR) : dL) : dR;
+    put(hasL, p, __dmul_rn(mL, kSixth));
+    p += hasL;
+    put(true, p, diag);
+    ++p;
+    put(hasR, p, __dmul_rn(mR, kSixth));
+    p += hasR;
     // a[i][P] = -int p dv/ds: -B^T (assembly.py:255)
-    if (a > 0) put(-1.0);
-    if (a < N) put(1.0);
+    put(hasL, p, -1.0);
+    p += hasL;
+    put(hasR, p, 1.0);
+    p += hasR;
     // multiplier columns (assembly.py:273,277); the cell's other flux dof stores an explicit 0.0
     const bool hu = t.z >= 0 && a <= 1, hv = t.w >= 0 && a >= N - 1;
     const double vu = a == 0 ? -1.0 : 0.0, vv = a == N ? 1.0 : 0.0;
-    if (hu && hv) {
-      const bool ufirst = t.z < t.w;
-      put(ufirst ? vu : vv);
-      put(ufirst ? vv : vu);
-    } else if (hu) {
-      put(vu);
-    } else if (hv) {
-      put(vv);
-    }
+    const bool ufirst = !hv || (hu && t.z < t.w);
+    put(hu || hv, p, (hu && ufirst) ? vu : vv);
+    put(hu && hv, p + 1, ufirst ? vv : vu);
     if (rhs) {
       // assembly.py:258-260: +p_bc at in_marker vertices (boundary END of an edge), -p_bc at
       // out_marker vertices (boundary START of an edge)
@@ -264,12 +297,13 @@ assemble_rows_kernel(Net g, Coef c, const int32_t* __restrict__ rowptr, double* 
     }
   } else if (r < g.loff) {
     // a[P][i] = +int phi dq/ds: B = [-1, +1] (assembly.py:254);  L[P] = int f phi (assembly.py:262)
-    put(-1.0);
-    put(1.0);
+    put(true, p, -1.0);
+    put(true, p + 1, 1.0);
     if (rhs) {
       double bv = 0.0;
       if (c.f_cell || c.f_const != 0.0) {
-        const int cell = r - g.poff, ce = cell / N, j = cell - ce * N;
+        const int cell = r - g.poff;
+        const int ce = N1 ? cell : fastdiv(cell, g.div_n), j = cell - ce * N;
         const int4 ct = g.slot_uvl[g.edge_slot[ce]];
         const double h = seg_length(load_vertex(g.x2, vertex_id(g, ce, ct.x, ct.y, j)),
                                     load_vertex(g.x2, vertex_id(g, ce, ct.x, ct.y, j + 1)));
@@ -279,20 +313,209 @@ assemble_rows_kernel(Net g, Coef c, const int32_t* __restrict__ rowptr, double* 
     }
   } else if (r < g.ndofs) {
     // a[LM][c] = +mu q at in-edges, -mu q at out-edges (assembly.py:272,276)
-    const int i0 = g.bif_ptr[r - g.loff], i1 = g.bif_ptr[r - g.loff + 1];
-    for (int k = i0; k < i1; ++k) {
+    for (int k = d.i0; k < d.i1; ++k) {
       const bool in = g.bif_inc[k] & 1;
-      put(in ? 0.0 : -1.0);
-      put(in ? 1.0 : 0.0);
+      put(true, p, in ? 0.0 : -1.0);
+      put(true, p + 1, in ? 1.0 : 0.0);
+      p += 2;
     }
     if (rhs && !ACC) b[r] = 0.0;
   }
-  __syncthreads();
-  if (lhs) {
-    const int m = min(tnnz, kTileCap);
-    for (int i = threadIdx.x; i < m; i += kTileRows) {
-      if (ACC) vals[(size_t)sbase + i] += sm[i]; else vals[(size_t)sbase + i] = sm[i];
+}
+
+// ---- region-specialised tiles -----------------------------------------------------------------
+// The rows of the three regions [flux | pressure | multiplier] are tiled separately, so a block
+// never mixes row types:
+//   flux tile      N == 1: one thread per graph EDGE emits both of its rows (no shuffles, no
+//                  divergence between the a=0 / a=1 lanes), 512 rows per block;
+//                  N >= 2: one thread per row with the warp-shuffle hand-over (assemble_row);
+//   pressure tile  rows are the constant pair {-1, +1}: 16-byte stores straight to HBM;
+//   multiplier tile the values are a function of the incidence list only: incidence-parallel.
+constexpr int kFluxRowsN1 = 512;
+constexpr int kAsmCap = 2560;  // 512 rows * 5 entries (N == 1)  >=  256 rows * 7 entries (N >= 2)
+constexpr int kPresRows = 512;
+constexpr int kLamRows = 256;
+
+template <bool ACC>
+__device__ __forceinline__ void store_pair(double* __restrict__ vals, size_t idx, double v0, double v1) {
+  // idx even => 16-byte aligned (vals comes from cudaMalloc)
+  if ((idx & 1) == 0) {
+    double2* dst = reinterpret_cast<double2*>(vals + idx);
+    double2 v = make_double2(v0, v1);
+    if (ACC) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+    *dst = v;
+  } else {
+    if (ACC) { vals[idx] += v0; vals[idx + 1] += v1; } else { vals[idx] = v0; vals[idx + 1] = v1; }
+  }
+}
+
+// coalesced 16-byte flush of a staged tile; entries were staged at sm[off + k], off = sbase & 1
+template <bool ACC>
+__device__ __forceinline__ void flush_tile(const double* sm, double* __restrict__ vals, int sbase, int tnnz) {
+  const int off = sbase & 1;
+  double* out = vals + sbase - off;
+  const int lo = off, hi = off + tnnz;
+  const int npair = (hi + 1) >> 1;
+  for (int q = threadIdx.x; q < npair; q += blockDim.x) {
+    const int i = 2 * q;
+    if (i >= lo && i + 1 < hi) {
+      double2 v = *reinterpret_cast<const double2*>(sm + i);
+      double2* dst = reinterpret_cast<double2*>(out + i);
+      if (ACC) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+      *dst = v;
+    } else {
+      if (i >= lo && i < hi) { if (ACC) out[i] += sm[i]; else out[i] = sm[i]; }
+      if (i + 1 >= lo && i + 1 < hi) { if (ACC) out[i + 1] += sm[i + 1]; else out[i + 1] = sm[i + 1]; }
     }
+  }
+}
+
+// N == 1 flux tile: thread <-> edge slot, rows 2*slot (vertex u) and 2*slot+1 (vertex v)
+template <bool ACC>
+__device__ __forceinline__ void flux_tile_n1(const Net& g, const Coef& c, const int32_t* __restrict__ rowptr,
+                                             double* __restrict__ vals, double* __restrict__ b, int lhs,
+                                             int rhs, int tile, double* sm) {
+  const int r0 = tile * kFluxRowsN1;
+  const int rend = min(r0 + kFluxRowsN1, g.nq);
+  const int sbase = rowptr[r0];
+  const int tnnz = rowptr[rend] - sbase;
+  const int r = r0 + 2 * threadIdx.x;
+  if (r < rend) {
+    const int slot = r >> 1;
+    const int4 t = g.slot_uvl[slot];
+    const int e = g.slot_edge[slot];
+    const int start = rowptr[r] - sbase;
+    const VertexRec v0 = load_vertex(g.x2, t.x), v1 = load_vertex(g.x2, t.y);
+    const double R = c.R_cell ? c.R_cell[e] : c.R_const;
+    const double m = __dmul_rn(R, seg_length(v0, v1));
+    c.cell_rh[e] = m;
+    if (rhs) {
+      // assembly.py:258-260: -p_bc at out_marker vertices (boundary START), +p_bc at in_marker (END)
+      const double b0 = t.z < 0 ? -v0.p : 0.0, b1 = t.w < 0 ? v1.p : 0.0;
+      double2* dst = reinterpret_cast<double2*>(b + r);  // r even
+      double2 v = make_double2(b0, b1);
+      if (ACC) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+      *dst = v;
+    }
+    if (lhs) {
+      const double m3 = __dmul_rn(m, kThird), m6 = __dmul_rn(m, kSixth);
+      const bool hu = t.z >= 0, hv = t.w >= 0;
+      const bool ufirst = !hv || (hu && t.z < t.w);
+      const int nl = (int)hu + (int)hv;
+      // row u: [m/3, m/6 | +1 | (lam_u: -1) (lam_v: 0)]; row v: [m/6, m/3 | -1 | (lam_u: 0) (lam_v: +1)]
+      const double u0 = (hu && ufirst) ? -1.0 : 0.0, u1 = ufirst ? 0.0 : -1.0;
+      const double w0 = (hu && ufirst) ? 0.0 : 1.0, w1 = ufirst ? 1.0 : 0.0;
+      if (tnnz <= kAsmCap) {
+        double* s0 = sm + (sbase & 1) + start;
+        double* s1 = s0 + 3 + nl;
+        s0[0] = m3; s0[1] = m6; s0[2] = 1.0;
+        s1[0] = m6; s1[1] = m3; s1[2] = -1.0;
+        if (nl > 0) { s0[3] = u0; s1[3] = w0; }
+        if (nl > 1) { s0[4] = u1; s1[4] = w1; }
+      }  // tnnz <= 512 rows * 5 entries == kAsmCap always holds for N == 1
+    }
+  }
+  if (lhs && tnnz <= kAsmCap) {
+    __syncthreads();
+    flush_tile<ACC>(sm, vals, sbase, tnnz);
+  }
+}
+
+// N >= 2 flux tile: thread <-> row
+template <bool ACC>
+__device__ __forceinline__ void flux_tile_gen(const Net& g, const Coef& c, const int32_t* __restrict__ rowptr,
+                                              double* __restrict__ vals, double* __restrict__ b, int lhs,
+                                              int rhs, int tile, double* sm) {
+  const int r0 = tile * kTileRows;
+  const int rend = min(r0 + kTileRows, g.nq);
+  const int r = r0 + threadIdx.x;
+  RowDesc d;
+  d.sbase = rowptr[r0];
+  d.tnnz = rowptr[rend] - d.sbase;
+  d.start = 0; d.a = 0; d.e = 0; d.i0 = d.i1 = 0;
+  d.t = make_int4(0, 0, -1, -1);
+  const bool active = r < rend;
+  if (active) {
+    d.start = rowptr[r] - d.sbase;
+    const int slot = fastdiv(r, g.div_np1);
+    d.a = r - slot * (g.N + 1);
+    d.t = g.slot_uvl[slot];
+    d.e = g.slot_edge[slot];
+  }
+  const int lane = threadIdx.x & 31;
+  const int rr = active ? r : g.ndofs;  // inactive lanes still take part in the shuffles
+  if (d.tnnz > kAsmCap) {
+    if (lhs) assemble_row<ACC, false>(g, c, d, rr, d.sbase + d.start, lane, b, rhs, GlobalSink<ACC>{vals});
+    else assemble_row<ACC, false>(g, c, d, rr, 0, lane, b, rhs, [](bool, int, double) {});
+    return;
+  }
+  assemble_row<ACC, false>(g, c, d, rr, (d.sbase & 1) + d.start, lane, b, rhs, SmemSink{sm});
+  if (lhs) {
+    __syncthreads();
+    flush_tile<ACC>(sm, vals, d.sbase, d.tnnz);
+  }
+}
+
+// pressure tile: a[P][i] = +int phi dq/ds: B = [-1, +1] (assembly.py:254); L[P] = int f phi (:262)
+template <bool ACC, bool N1>
+__device__ __forceinline__ void pressure_tile(const Net& g, const Coef& c, const int32_t* __restrict__ rowptr,
+                                              double* __restrict__ vals, double* __restrict__ b, int lhs,
+                                              int rhs, int tile) {
+  const int r0 = g.poff + tile * kPresRows;
+  const int rend = min(r0 + kPresRows, g.loff);
+  const int sbase = rowptr[r0];  // every pressure row has exactly two entries
+  const int N = N1 ? 1 : g.N;
+  for (int r = r0 + threadIdx.x; r < rend; r += blockDim.x) {
+    if (lhs) store_pair<ACC>(vals, (size_t)sbase + 2 * (size_t)(r - r0), -1.0, 1.0);
+    if (rhs) {
+      double bv = 0.0;
+      if (c.f_cell || c.f_const != 0.0) {
+        const int cell = r - g.poff;
+        const int ce = N1 ? cell : fastdiv(cell, g.div_n), j = cell - ce * N;
+        const int4 ct = g.slot_uvl[g.edge_slot[ce]];
+        const double h = seg_length(load_vertex(g.x2, vertex_id(g, ce, ct.x, ct.y, j)),
+                                    load_vertex(g.x2, vertex_id(g, ce, ct.x, ct.y, j + 1)));
+        bv = __dmul_rn(c.f_cell ? c.f_cell[cell] : c.f_const, h);
+      }
+      if (ACC) b[r] += bv; else b[r] = bv;
+    }
+  }
+}
+
+// multiplier tile: a[LM][c] = +mu q at in-edges, -mu q at out-edges (assembly.py:272,276); the
+// touching cell's other flux dof stores an explicit 0.0.  Incidence k of the tile owns the pair
+// at 2*(k - k0): in-edge (0, +1), out-edge (-1, 0).
+template <bool ACC>
+__device__ __forceinline__ void lambda_tile(const Net& g, const int32_t* __restrict__ rowptr,
+                                            double* __restrict__ vals, double* __restrict__ b, int lhs,
+                                            int rhs, int tile) {
+  const int i0 = tile * kLamRows;
+  const int i1 = min(i0 + kLamRows, g.n_bif);
+  if (lhs) {
+    const int k0 = g.bif_ptr[i0], k1 = g.bif_ptr[i1];
+    const int sbase = rowptr[g.loff + i0];
+    for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+      const bool in = g.bif_inc[k] & 1;
+      store_pair<ACC>(vals, (size_t)sbase + 2 * (size_t)(k - k0), in ? 0.0 : -1.0, in ? 1.0 : 0.0);
+    }
+  }
+  if (rhs && !ACC)
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) b[g.loff + i] = 0.0;
+}
+
+template <bool ACC, bool N1>
+__global__ void __launch_bounds__(kTileRows)
+assemble_tiles_kernel(Net g, Coef c, const int32_t* __restrict__ rowptr, double* __restrict__ vals,
+                      double* __restrict__ b, int lhs, int rhs, int n_flux_tiles, int n_pres_tiles) {
+  __shared__ __align__(16) double sm[kAsmCap + 2];
+  const int t = blockIdx.x;
+  if (t < n_flux_tiles) {
+    if (N1) flux_tile_n1<ACC>(g, c, rowptr, vals, b, lhs, rhs, t, sm);
+    else flux_tile_gen<ACC>(g, c, rowptr, vals, b, lhs, rhs, t, sm);
+  } else if (t < n_flux_tiles + n_pres_tiles) {
+    pressure_tile<ACC, N1>(g, c, rowptr, vals, b, lhs, rhs, t - n_flux_tiles);
+  } else {
+    lambda_tile<ACC>(g, rowptr, vals, b, lhs, rhs, t - n_flux_tiles - n_pres_tiles);
   }
 }
 

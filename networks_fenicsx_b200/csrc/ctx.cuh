@@ -39,6 +39,8 @@ struct DevBuf {
 struct TreeSchedule {
   bool set = false;
   int n_chunks = 0, n_lvl_ptr = 0, n_chords = 0;
+  DevBuf<int32_t> bif_of_t;
+  DevBuf<double> lam_nat;
   DevBuf<int32_t> t_of_bif, t_parent, t_pedge, t_cptr, t_cidx, chunk_lptr, lvl_ptr, chord_edge;
   std::vector<int32_t> chunk_lptr_h, lvl_ptr_h;
   // numeric

@@ -28,6 +28,8 @@ Net make_net(const nxfx_ctx* c) {
   g.poff = (int32_t)c->poff;
   g.loff = (int32_t)c->loff;
   g.ndofs = (int32_t)c->ndofs;
+  g.div_np1 = make_fastdiv((uint32_t)c->N + 1);
+  g.div_n = make_fastdiv((uint32_t)std::max(c->N, 2));
   g.slot_uvl = c->slot_uvl.p;
   g.slot_edge = c->slot_edge.p;
   g.edge_slot = c->edge_slot.p;
@@ -41,6 +43,8 @@ TreeDev make_tree(nxfx_ctx* c) {
   TreeDev t;
   auto& s = c->tree;
   t.t_of_bif = s.t_of_bif.p;
+  t.bif_of_t = s.bif_of_t.p;
+  t.lam_nat = s.lam_nat.p;
   t.t_parent = s.t_parent.p;
   t.t_pedge = s.t_pedge.p;
   t.t_cptr = s.t_cptr.p;
@@ -93,7 +97,10 @@ int build_vertices(nxfx_ctx* ctx) {
 
 // ---- solver building blocks ------------------------------------------------------------------
 constexpr size_t kPipeSmem = kStages * sizeof(SpmvStage) + kStages * sizeof(uint64_t);
-constexpr int kPipeBlocksPerSM = 3;
+#ifndef NXFX_SPMV_BLOCKS
+#define NXFX_SPMV_BLOCKS 5
+#endif
+constexpr int kPipeBlocksPerSM = NXFX_SPMV_BLOCKS;
 
 int do_spmv(nxfx_ctx* ctx, const double* x, double* y) {
   const int ntiles = (int)cdiv(ctx->ndofs, kTileRows);
@@ -181,6 +188,8 @@ int do_multi_axpy(nxfx_ctx* ctx, int n, int k, const double* A, size_t stride, c
   return NXFX_OK;
 }
 
+int ensure_work(nxfx_ctx* ctx, size_t nvec);
+
 int tree_pass(nxfx_ctx* ctx, bool factor) {
   auto& s = ctx->tree;
   TreeDev t = make_tree(ctx);
@@ -221,8 +230,16 @@ int do_pc_setup(nxfx_ctx* ctx) {
   return NXFX_OK;
 }
 
-int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z) {
+int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add = false) {
   const int n = (int)ctx->ndofs;
+  if (add && pc_type != NXFX_PC_NETWORK_SCHUR) {  // generic: z_tmp = P^{-1} r, z += z_tmp
+    int rc = ensure_work(ctx, 3);
+    if (rc) return rc;
+    double* tmp = ctx->work.p + 2 * (size_t)n;
+    if ((rc = do_pc_apply(ctx, pc_type, r, tmp, false))) return rc;
+    NXFX_LAUNCH(ctx, add_kernel, vec_grid(ctx, n), kThreads, 0, n, tmp, z);
+    return NXFX_OK;
+  }
   if (pc_type == NXFX_PC_NONE) {
     NXFX_CUDA(ctx, cudaMemcpyAsync(z, r, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     return NXFX_OK;
@@ -243,8 +260,11 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z) {
     int rc = tree_pass(ctx, false);
     if (rc) return rc;
   }
-  NXFX_LAUNCH(ctx, edge_backsub_kernel, (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads), kThreads, 0,
-              g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+  const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
+  if (add)
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+  else
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
   return NXFX_OK;
 }
 
@@ -260,28 +280,40 @@ void push_history(nxfx_solve_info* info, double v) {
   if (info->history_len < NXFX_HISTORY_LEN) info->history[info->history_len++] = v;
 }
 
-// x = P^{-1} b followed by `refine_steps` steps of iterative refinement; one sync at the end.
+// x = P^{-1} b followed by `refine_steps` steps of iterative refinement x += P^{-1}(b - A x); the
+// residual kernel also returns ||b||^2, the back-substitution updates x in place; one sync at the
+// end.  The reported residual is the last one computed: the true final residual when
+// opts->final_residual is set, otherwise the residual of the iterate BEFORE the last correction
+// (an upper estimate; KSPPREONLY itself computes none).
 int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts* o, nxfx_solve_info* info) {
   const int n = (int)ctx->ndofs;
-  int rc = ensure_work(ctx, 2);
+  int rc = ensure_work(ctx, 3);
   if (rc) return rc;
   double* r = ctx->work.p;
-  double* z = ctx->work.p + n;
   const int steps = std::max(0, std::min(o->refine_steps, 32));
-  if ((rc = do_multi_dot(ctx, n, 1, b, 0, b, slot(ctx, 0)))) return rc;
-  if ((rc = do_pc_apply(ctx, o->pc_type, b, x))) return rc;
+  if ((rc = do_pc_apply(ctx, o->pc_type, b, x, false))) return rc;
+  int nres = 0;
   for (int s = 0; s < steps; ++s) {
-    if ((rc = do_residual(ctx, b, x, r, slot(ctx, 1 + s)))) return rc;
-    if ((rc = do_pc_apply(ctx, o->pc_type, r, z))) return rc;
-    NXFX_LAUNCH(ctx, add_kernel, vec_grid(ctx, n), kThreads, 0, n, z, x);
+    if ((rc = do_residual(ctx, b, x, r, slot(ctx, 2 * nres)))) return rc;
+    ++nres;
+    if ((rc = do_pc_apply(ctx, o->pc_type, r, x, true))) return rc;
   }
-  if ((rc = do_residual(ctx, b, x, r, slot(ctx, 1 + steps)))) return rc;
-  NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, slot(ctx, 0), (steps + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  info->rhs_norm = std::sqrt(ctx->scal_h[0]);
-  for (int s = 0; s <= steps; ++s) push_history(info, std::sqrt(ctx->scal_h[1 + s]));
-  info->residual_norm = std::sqrt(ctx->scal_h[1 + steps]);
+  if (o->final_residual) {
+    if ((rc = do_residual(ctx, b, x, r, slot(ctx, 2 * nres)))) return rc;
+    ++nres;
+  }
   info->iterations = 1 + steps;
+  if (nres == 0) {  // nothing measured: plain preconditioner application
+    NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    info->rhs_norm = info->residual_norm = -1.0;
+    info->converged = 1;
+    return NXFX_OK;
+  }
+  NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, slot(ctx, 0), 2 * nres * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  info->rhs_norm = std::sqrt(ctx->scal_h[1]);
+  for (int s = 0; s < nres; ++s) push_history(info, std::sqrt(ctx->scal_h[2 * s]));
+  info->residual_norm = std::sqrt(ctx->scal_h[2 * (nres - 1)]);
   const double tol = std::max(o->rtol * info->rhs_norm, o->atol);
   info->converged = std::isfinite(info->residual_norm) && info->residual_norm <= tol;
   return NXFX_OK;
@@ -305,16 +337,15 @@ int solve_fgmres(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opt
   std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gvec(m + 1), y(m);
 
   NXFX_CUDA(ctx, cudaMemsetAsync(x, 0, n * sizeof(double), ctx->stream));
-  if ((rc = do_multi_dot(ctx, n, 1, b, 0, b, slot(ctx, 0)))) return rc;
   int its = 0;
   const int max_it = o->max_it > 0 ? o->max_it : 10000;
   double tol = 0.0;
   while (true) {
     if ((rc = do_residual(ctx, b, x, r, slot(ctx, 1)))) return rc;
-    NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, slot(ctx, 0), 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, slot(ctx, 1), 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    info->rhs_norm = std::sqrt(ctx->scal_h[0]);
-    const double beta = std::sqrt(ctx->scal_h[1]);
+    info->rhs_norm = std::sqrt(ctx->scal_h[1]);
+    const double beta = std::sqrt(ctx->scal_h[0]);
     tol = std::max(o->rtol * info->rhs_norm, o->atol);
     info->residual_norm = beta;
     push_history(info, beta);
@@ -635,11 +666,18 @@ int nxfx_assemble(nxfx_ctx* ctx, const double* R_cell, double R_const, const dou
   Coef c;
   c.R_cell = R_cell; c.f_cell = f_cell; c.R_const = R_const; c.f_const = f_const;
   c.cell_rh = ctx->cell_rh.p;
-  const int grid = (int)cdiv(ctx->ndofs, kTileRows);
-  if (accumulate)
-    NXFX_LAUNCH(ctx, assemble_rows_kernel<true>, grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs);
-  else
-    NXFX_LAUNCH(ctx, assemble_rows_kernel<false>, grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs);
+  const bool n1 = ctx->N == 1;
+  const int nft = (int)cdiv(ctx->nq, n1 ? kFluxRowsN1 : kTileRows);
+  const int npt = (int)cdiv(ctx->nc, kPresRows);
+  const int nlt = (int)cdiv(ctx->n_bif, kLamRows);
+  const int grid = nft + npt + nlt;
+  if (accumulate) {
+    if (n1) NXFX_LAUNCH(ctx, (assemble_tiles_kernel<true, true>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs, nft, npt);
+    else NXFX_LAUNCH(ctx, (assemble_tiles_kernel<true, false>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs, nft, npt);
+  } else {
+    if (n1) NXFX_LAUNCH(ctx, (assemble_tiles_kernel<false, true>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs, nft, npt);
+    else NXFX_LAUNCH(ctx, (assemble_tiles_kernel<false, false>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs, nft, npt);
+  }
   if (lhs) { ctx->assembled = true; ctx->pc_ready = false; }
   return NXFX_OK;
 }
@@ -664,6 +702,13 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
   }
   int rc;
   if ((rc = upload(ctx, s.t_of_bif, t_of_bif, nb))) return rc;
+  std::vector<int32_t> inv(nb);
+  for (size_t i = 0; i < nb; ++i) {
+    if (t_of_bif[i] < 0 || (size_t)t_of_bif[i] >= nb) return fail(ctx, NXFX_ERR_INVALID, "t_of_bif out of range");
+    inv[t_of_bif[i]] = (int32_t)i;
+  }
+  if ((rc = upload(ctx, s.bif_of_t, inv.data(), nb))) return rc;
+  NXFX_CUDA(ctx, s.lam_nat.alloc(nb));
   if ((rc = upload(ctx, s.t_parent, t_parent, nb))) return rc;
   if ((rc = upload(ctx, s.t_pedge, t_pedge, nb))) return rc;
   if ((rc = upload(ctx, s.t_cptr, t_cptr, nb + 1))) return rc;

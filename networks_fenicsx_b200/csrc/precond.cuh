@@ -22,6 +22,7 @@ namespace nxfx {
 
 struct TreeDev {
   const int32_t* __restrict__ t_of_bif;
+  const int32_t* __restrict__ bif_of_t;
   const int32_t* __restrict__ t_parent;
   const int32_t* __restrict__ t_pedge;
   const int32_t* __restrict__ t_cptr;
@@ -33,7 +34,8 @@ struct TreeDev {
   double* d;
   double* gd;
   double* r;
-  double* lam;
+  double* lam;      // schedule order
+  double* lam_nat;  // natural (bifurcation) order, read by the back-substitution
 };
 
 // g_e = 1 / sum_j R_j h_j
@@ -102,6 +104,7 @@ tree_sweep_kernel(TreeDev t, const double* __restrict__ edge_g, int chunk0) {
         double v = t.r[n] / t.d[n];
         if (p >= 0) v += t.gd[n] * t.lam[p];
         t.lam[n] = v;
+        t.lam_nat[t.bif_of_t[n]] = v;
       }
       __syncthreads();
     }
@@ -212,7 +215,10 @@ __device__ __forceinline__ void tree_chunk(const TreeDev& t, TreeSmem& S, int ch
       }
       __syncthreads();
     }
-    for (int i = tid; i < nn; i += nth) t.lam[b0 + i] = S.a[i];
+    for (int i = tid; i < nn; i += nth) {
+      t.lam[b0 + i] = S.a[i];
+      t.lam_nat[t.bif_of_t[b0 + i]] = S.a[i];
+    }
   }
 }
 
@@ -274,6 +280,8 @@ bif_rhs_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* __r
 }
 
 // Back-substitution: q_a = q_0 + F_a ; p_0 = r_q0 + lam_u - (Mq)_0 ; p_a = p_{a-1} + r_qa - (Mq)_a
+// ADD: z += P^{-1} r (iterative refinement updates x in place).
+template <bool ADD>
 __global__ void __launch_bounds__(kThreads)
 edge_backsub_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh,
                     const double* __restrict__ r, const double* __restrict__ edge_g,
@@ -281,14 +289,14 @@ edge_backsub_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh,
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= g.E) {
     const int i = idx - g.E;
-    if (i < g.n_bif) z[g.loff + i] = t.lam[t.t_of_bif[i]];
+    if (i < g.n_bif) { if (ADD) z[g.loff + i] += t.lam_nat[i]; else z[g.loff + i] = t.lam_nat[i]; }
     return;
   }
   const int e = idx, N = g.N;
   const int slot = g.edge_slot[e];
   const int4 uv = g.slot_uvl[slot];
-  const double lu = uv.z >= 0 ? t.lam[t.t_of_bif[uv.z]] : 0.0;
-  const double lv = uv.w >= 0 ? t.lam[t.t_of_bif[uv.w]] : 0.0;
+  const double lu = uv.z >= 0 ? t.lam_nat[uv.z] : 0.0;
+  const double lv = uv.w >= 0 ? t.lam_nat[uv.w] : 0.0;
   const double* rq = r + (size_t)slot * (N + 1);
   const double* rp = r + g.poff + (size_t)e * N;
   const double* rh = cell_rh + (size_t)e * N;
@@ -297,7 +305,7 @@ edge_backsub_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh,
   const double q0 = edge_g[e] * (edge_c[e] + lu - lv);
   double F = 0.0, qprev = 0.0, qa = q0, hl = 0.0, p = lu;
   for (int a = 0; a <= N; ++a) {
-    zq[a] = qa;
+    if (ADD) zq[a] += qa; else zq[a] = qa;
     double qn = 0.0, hr = 0.0;
     if (a < N) {
       F += rp[a];
@@ -305,7 +313,7 @@ edge_backsub_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh,
       hr = rh[a];
       const double Mq = hl * (qprev * kSixth + qa * kThird) + hr * (qa * kThird + qn * kSixth);
       p += rq[a] - Mq;
-      zp[a] = p;
+      if (ADD) zp[a] += p; else zp[a] = p;
     }
     qprev = qa;
     qa = qn;

@@ -64,8 +64,8 @@ __device__ __forceinline__ void finish_partials(double (&mine)[K], double* parti
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
-// MODE 0: y = A x.   MODE 1: y = b - A x, block partials of ||y||^2 -> norm2_out (grid-strided
-// tiles so that the partial count stays bounded).
+// MODE 0: y = A x.   MODE 1: y = b - A x and norm2_out[0] = ||y||^2, norm2_out[1] = ||b||^2
+// (block partials, grid-strided tiles so that the partial count stays bounded).
 template <int MODE>
 __global__ void __launch_bounds__(kTileRows)
 spmv_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
@@ -75,7 +75,7 @@ spmv_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
   __shared__ double sm[kTileCap];
   __shared__ int srow[kTileRows + 1];
   __shared__ double red[kTileRows / 32];
-  double nrm = 0.0;
+  double nrm = 0.0, nrb = 0.0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int r0 = tile * kTileRows;
     const int nr = min(kTileRows, n - r0);
@@ -115,15 +115,17 @@ spmv_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
       if (MODE == 0) {
         y[r0 + threadIdx.x] = acc;
       } else {
-        const double r = __dsub_rn(b[r0 + threadIdx.x], acc);
+        const double bi = b[r0 + threadIdx.x];
+        const double r = __dsub_rn(bi, acc);
         y[r0 + threadIdx.x] = r;
         nrm += r * r;
+        nrb += bi * bi;
       }
     }
   }
   if (MODE == 1) {
-    double mine[1] = {block_sum<kTileRows>(nrm, red)};
-    finish_partials<kTileRows, 1>(mine, partial, gridDim.x, ticket, norm2_out, red);
+    double mine[2] = {block_sum<kTileRows>(nrm, red), block_sum<kTileRows>(nrb, red)};
+    finish_partials<kTileRows, 2>(mine, partial, gridDim.x, ticket, norm2_out, red);
   }
 }
 
@@ -134,7 +136,10 @@ spmv_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
 // only gather x, multiply in place and reduce rows, so HBM streaming never waits for the gather /
 // reduce phases of the same block.
 constexpr int kPipeCap = 1792;  // entries per stage = 7 * kTileRows
-constexpr int kStages = 3;
+#ifndef NXFX_SPMV_STAGES
+#define NXFX_SPMV_STAGES 2
+#endif
+constexpr int kStages = NXFX_SPMV_STAGES;
 
 struct alignas(128) SpmvStage {
   double vals[kPipeCap];
@@ -221,7 +226,7 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
       if (tile < ntiles) issue(tile, k);
     }
   }
-  double nrm = 0.0;
+  double nrm = 0.0, nrb = 0.0;
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int s = it % kStages;
@@ -271,6 +276,7 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
         const double r = __dsub_rn(bi, acc);
         y[r0 + tid] = r;
         nrm += r * r;
+        nrb += bi * bi;
       }
     }
     // order this thread's generic-proxy accesses to the stage before the TMA refill
@@ -278,8 +284,8 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
     __syncthreads();
   }
   if (MODE == 1) {
-    double mine[1] = {block_sum<kTileRows>(nrm, red)};
-    finish_partials<kTileRows, 1>(mine, partial, gridDim.x, ticket, norm2_out, red);
+    double mine[2] = {block_sum<kTileRows>(nrm, red), block_sum<kTileRows>(nrb, red)};
+    finish_partials<kTileRows, 2>(mine, partial, gridDim.x, ticket, norm2_out, red);
   }
 }
 

@@ -29,7 +29,8 @@ class Solver:
         assembler: The hydraulic network assembler.
         petsc_options_prefix: Prefix for the options (kept for compatibility).
         petsc_options: Dictionary of PETSc-style options, see :class:`la.KSP`. Extra keys:
-            ``nxfx_refine_steps`` (iterative-refinement steps of the direct solve, default 1).
+            ``nxfx_refine_steps`` (iterative-refinement steps of the direct solve, default 1),
+            ``nxfx_final_residual`` (also evaluate the true residual of the final iterate).
         kind: ``None``/``"mpi"`` (monolithic AIJ) or ``"nest"``.
     """
 
@@ -131,13 +132,15 @@ class Solver:
             opts.ksp_type = _lib.KSP_FGMRES
         else:
             raise ValueError(f"unsupported ksp_type {ksp_type!r}")
-        default_rtol = 1e-13 if ksp_type == "preonly" else 1e-5  # PETSc default rtol for Krylov types
+        # preonly: the checked residual is the one BEFORE the last refinement correction
+        default_rtol = 1e-10 if ksp_type == "preonly" else 1e-5  # 1e-5: PETSc default for Krylov types
         opts.rtol = float(o.get("ksp_rtol", default_rtol))
         opts.atol = float(o.get("ksp_atol", 1e-50 if ksp_type != "preonly" else 1e-300))
         opts.max_it = int(o.get("ksp_max_it", 10000))
         opts.restart = int(o.get("ksp_gmres_restart", 30))
         opts.refine_steps = int(o.get("nxfx_refine_steps", 1))
         opts.error_if_not_converged = int(bool(o.get("ksp_error_if_not_converged", False)))
+        opts.final_residual = int(bool(o.get("nxfx_final_residual", False)))
         return opts
 
     # ---- solve --------------------------------------------------------------------------------
