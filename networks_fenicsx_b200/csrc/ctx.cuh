@@ -39,13 +39,15 @@ struct DevBuf {
 struct TreeSchedule {
   bool set = false;
   int n_chunks = 0, n_lvl_ptr = 0, n_chords = 0;
-  DevBuf<int32_t> bif_of_t;
+  DevBuf<int32_t> bif_of_t, chunk_desc;
   DevBuf<double> lam_nat;
   DevBuf<int32_t> t_of_bif, t_parent, t_pedge, t_cptr, t_cidx, chunk_lptr, lvl_ptr, chord_edge;
   std::vector<int32_t> chunk_lptr_h, lvl_ptr_h;
   // numeric
   DevBuf<double> diag0, tg, d, gd, r, lam;  // schedule order
   bool fast_ok = false;                       // every chunk fits the shared-memory sweep kernel
+  bool coop_ok = false;                       // all bottom chunks can be co-resident (single-launch solve)
+  unsigned int epoch = 0;
 };
 
 }  // namespace nxfx
@@ -76,7 +78,7 @@ struct nxfx_ctx {
   nxfx::DevBuf<double> edge_g, edge_c, edge_fn;  // [E] conductance, condensed rhs, F_N
   nxfx::DevBuf<double> work;                     // krylov vectors
   nxfx::DevBuf<double> scal;                     // device scalars / partials
-  nxfx::DevBuf<unsigned int> ticket;  // [0] reductions, [1] tree sweeps
+  nxfx::DevBuf<unsigned int> ticket;  // [0] reductions, [1] tree sweeps, [2] tree epoch flag
   double* scal_h = nullptr;  // pinned mirror
   // e2e staging
   nxfx::DevBuf<double> e2e_pbc, e2e_b, e2e_x;

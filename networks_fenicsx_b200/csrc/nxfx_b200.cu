@@ -44,6 +44,7 @@ TreeDev make_tree(nxfx_ctx* c) {
   auto& s = c->tree;
   t.t_of_bif = s.t_of_bif.p;
   t.bif_of_t = s.bif_of_t.p;
+  t.chunk_desc = s.chunk_desc.p;
   t.lam_nat = s.lam_nat.p;
   t.t_parent = s.t_parent.p;
   t.t_pedge = s.t_pedge.p;
@@ -75,8 +76,8 @@ int ensure_scal(nxfx_ctx* ctx) {
   if (ctx->scal.p) return NXFX_OK;
   NXFX_CUDA(ctx, ctx->scal.alloc(kScalPartials + kScalSlots));
   NXFX_CUDA(ctx, cudaMemsetAsync(ctx->scal.p, 0, (kScalPartials + kScalSlots) * sizeof(double), ctx->stream));
-  NXFX_CUDA(ctx, ctx->ticket.alloc(2));
-  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->ticket.p, 0, 2 * sizeof(unsigned int), ctx->stream));
+  NXFX_CUDA(ctx, ctx->ticket.alloc(4));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->ticket.p, 0, 4 * sizeof(unsigned int), ctx->stream));
   NXFX_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->scal_h), kScalSlots * sizeof(double), cudaHostAllocDefault));
   return NXFX_OK;
 }
@@ -196,11 +197,20 @@ int tree_pass(nxfx_ctx* ctx, bool factor) {
   const int nb = s.n_chunks - 1;  // bottom chunks; the last chunk is the top of the forest
   if (s.fast_ok) {
     const int grid = std::max(nb, 1);
+    unsigned int* tk = ctx->ticket.p + 1;
     if (factor) {
-      NXFX_LAUNCH(ctx, tree_fused_kernel<kTreeFactor>, grid, 1024, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1);
+      NXFX_LAUNCH(ctx, tree_factor_kernel, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk);
+    } else if (s.coop_ok && nb > 0) {
+      unsigned int* fl = ctx->ticket.p + 2;
+      unsigned int ep = ++s.epoch;
+      int nbv = nb;
+      void* args[] = {&t, &nbv, &tk, &fl, &ep};
+      NXFX_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tree_solve_coop_kernel), dim3(nb), dim3(kTreeThreads),
+                                                 args, sizeof(TreeSmem), ctx->stream));
+      ctx->launches++;
     } else {
-      NXFX_LAUNCH(ctx, tree_fused_kernel<kTreeUp>, grid, 1024, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1);
-      if (nb > 0) NXFX_LAUNCH(ctx, tree_fused_kernel<kTreeDown>, nb, 1024, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1);
+      NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk);
+      if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, tk);
     }
     return NXFX_OK;
   }
@@ -724,9 +734,30 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
     if (l1 - l0 > kLevelCap || lvl_ptr[l1] - lvl_ptr[l0] > kChunkCap) s.fast_ok = false;
   }
   if (s.fast_ok) {
-    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_fused_kernel<kTreeFactor>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
-    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_fused_kernel<kTreeUp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
-    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_fused_kernel<kTreeDown>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
+    std::vector<int32_t> desc((size_t)n_chunks * kDescInts, 0);
+    for (int c = 0; c < n_chunks; ++c) {
+      int32_t* d = desc.data() + (size_t)c * kDescInts;
+      const int l0 = chunk_lptr[c], l1 = chunk_lptr[c + 1];
+      d[0] = lvl_ptr[l0]; d[1] = lvl_ptr[l1]; d[2] = t_cptr[d[0]]; d[3] = t_cptr[d[1]]; d[4] = l1 - l0;
+      int lw = -1;  // levels 0..lw have <= 32 nodes: handled by one warp
+      while (lw + 1 < l1 - l0 && lvl_ptr[l0 + lw + 2] - lvl_ptr[l0 + lw + 1] <= 32) ++lw;
+      d[5] = lw;
+      for (int l = l0; l <= l1; ++l) d[8 + l - l0] = lvl_ptr[l];
+    }
+    if ((rc = upload(ctx, s.chunk_desc, desc.data(), desc.size()))) return rc;
+    NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // single-launch solve: needs every bottom chunk resident at once
+    s.coop_ok = false;
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    if (coop && cudaFuncSetAttribute(tree_solve_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(TreeSmem)) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_solve_coop_kernel, kTreeThreads, sizeof(TreeSmem)) == cudaSuccess)
+      s.coop_ok = (n_chunks - 1) <= per_sm * ctx->sm_count;
+    cudaGetLastError();
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_solve_kernel<kTreeUp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_solve_kernel<kTreeDown>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
   }
   NXFX_CUDA(ctx, s.tg.alloc(nb));
   NXFX_CUDA(ctx, s.diag0.alloc(nb));

@@ -29,6 +29,7 @@ struct TreeDev {
   const int32_t* __restrict__ t_cidx;
   const int32_t* __restrict__ chunk_lptr;
   const int32_t* __restrict__ lvl_ptr;
+  const int32_t* __restrict__ chunk_desc;  // [n_chunks][kDescInts]: {b0, b1, cb, ce, nl, lvl[0..nl]}
   double* diag0;
   double* tg;  // conductance of the link to the parent (0 for roots)
   double* d;
@@ -60,7 +61,8 @@ bif_diag_kernel(Net g, TreeDev t, const double* __restrict__ edge_g) {
   t.tg[n] = pe >= 0 ? edge_g[pe] : 0.0;
 }
 
-// MODE 0: numeric factorisation  d_t = diag0_t - sum_c g_c^2/d_c ; gd_t = g_t/d_t
+// Generic (global-memory) sweeps for schedules that do not fit the shared-memory kernels.
+// MODE 0: numeric factorisation  d_t = diag0_t - sum_c g_c^2/d_c ; gd_t = g_t/d_t ; t.d <- 1/d_t
 // MODE 1: forward (leaf -> root)  r_t += sum_c gd_c r_c
 // MODE 2: backward (root -> leaf) lam_t = r_t/d_t + gd_t lam_parent
 // MODE 3: forward then backward (top chunk)
@@ -81,7 +83,7 @@ tree_sweep_kernel(TreeDev t, const double* __restrict__ edge_g, int chunk0) {
             const int c = t.t_cidx[k];
             dd -= edge_g[t.t_pedge[c]] * t.gd[c];
           }
-          t.d[n] = dd;
+          t.d[n] = 1.0 / dd;  // the solve multiplies by 1/d
           const int pe = t.t_pedge[n];
           t.gd[n] = pe >= 0 ? edge_g[pe] / dd : 0.0;
         } else {
@@ -101,7 +103,7 @@ tree_sweep_kernel(TreeDev t, const double* __restrict__ edge_g, int chunk0) {
       const int b = t.lvl_ptr[L], e = t.lvl_ptr[L + 1];
       for (int n = b + threadIdx.x; n < e; n += blockDim.x) {
         const int p = t.t_parent[n];
-        double v = t.r[n] / t.d[n];
+        double v = t.r[n] * t.d[n];
         if (p >= 0) v += t.gd[n] * t.lam[p];
         t.lam[n] = v;
         t.lam_nat[t.bif_of_t[n]] = v;
@@ -113,17 +115,26 @@ tree_sweep_kernel(TreeDev t, const double* __restrict__ edge_g, int chunk0) {
 
 // ---- shared-memory tree sweeps ------------------------------------------------------------------
 // One thread block per bottom chunk: the chunk's node data, child lists and level table are staged
-// in shared memory once, the level loop then runs on-chip (a level costs a __syncthreads, not an
-// HBM/L2 round trip).  The block that finishes last (atomic ticket) also eliminates the top chunk
-// -- and for the solve runs its back-substitution -- so a sweep is ONE launch; the bottom chunks'
-// back-substitution is a second launch.
+// in shared memory once, the level loop then runs on-chip.  Per-level latency is what bounds these
+// kernels, so (i) the factorisation stores 1/d (no division on the dependent chain of the solve),
+// (ii) levels with <= 32 nodes at the shallow end of a chunk are handled by ONE warp with
+// __syncwarp instead of a block barrier, (iii) blocks are small (256 threads).
+// The block that finishes last (atomic ticket) eliminates the top chunk.  For the solve, all blocks
+// are co-resident (cooperative launch): they wait on an epoch flag for the top chunk and then
+// back-substitute their chunk straight from shared memory -- one launch per preconditioner
+// application.  Trees with more chunks than resident blocks use two launches (up, down).
 constexpr int kChunkCap = 2048;  // nodes per chunk held in shared memory
 constexpr int kLevelCap = 64;    // levels per chunk held in shared memory
+constexpr int kDescInts = 8 + kLevelCap + 1;  // {b0, b1, cb, ce, nl, Lw, -, -, lvl[0..nl]}
+#ifndef NXFX_TREE_THREADS
+#define NXFX_TREE_THREADS 1024
+#endif
+constexpr int kTreeThreads = NXFX_TREE_THREADS;
 
 struct TreeSmem {
-  double a[kChunkCap];  // F: d      U: r      D: lam
-  double b[kChunkCap];  // F: tg     U: d(top) D: d
-  double c[kChunkCap];  // F: gd     U: gd     D: gd
+  double a[kChunkCap];  // F: d -> 1/d   solve: r -> lam
+  double b[kChunkCap];  // F: tg         solve: 1/d
+  double c[kChunkCap];  // F: gd         solve: gd
   int cptr[kChunkCap + 1];
   int cidx[kChunkCap];
   int par[kChunkCap];
@@ -133,113 +144,239 @@ struct TreeSmem {
 
 enum { kTreeFactor = 0, kTreeUp = 1, kTreeDown = 2 };
 
-template <int MODE>
-__device__ __forceinline__ void tree_chunk(const TreeDev& t, TreeSmem& S, int chunk, bool top) {
-  const int tid = threadIdx.x, nth = blockDim.x;
-  const int L0 = t.chunk_lptr[chunk], L1 = t.chunk_lptr[chunk + 1];
-  const int nl = L1 - L0;
-  for (int i = tid; i <= nl; i += nth) S.lvl[i] = t.lvl_ptr[L0 + i];
-  __syncthreads();
-  const int b0 = S.lvl[0], b1 = S.lvl[nl], nn = b1 - b0;
-  if (MODE != kTreeDown) {
-    const int cb = t.t_cptr[b0], ce = t.t_cptr[b1];
-    for (int i = tid; i <= nn; i += nth) S.cptr[i] = t.t_cptr[b0 + i] - cb;
-    for (int i = tid; i < ce - cb; i += nth) S.cidx[i] = t.t_cidx[cb + i];
+struct ChunkInfo {
+  int b0, b1, cb, ce, nl, Lw;  // Lw: levels 0..Lw all have <= 32 nodes (warp phase), -1 if none
+};
+
+__device__ __forceinline__ ChunkInfo load_chunk_info(const TreeDev& t, int chunk, TreeSmem& S) {
+  const int32_t* __restrict__ desc = t.chunk_desc + (size_t)chunk * kDescInts;
+  ChunkInfo ci{desc[0], desc[1], desc[2], desc[3], desc[4], desc[5]};
+  for (int i = threadIdx.x; i <= ci.nl; i += blockDim.x) S.lvl[i] = desc[8 + i];
+  return ci;
+}
+
+// leaf -> root over the chunk's levels: block phase for the wide levels, one warp for the narrow top
+template <typename NodeOp>
+__device__ __forceinline__ void sweep_up(const TreeSmem& S, const ChunkInfo& ci, NodeOp op) {
+  const int tid = threadIdx.x;
+  for (int L = ci.nl - 1; L > ci.Lw; --L) {
+    for (int n = S.lvl[L] + tid; n < S.lvl[L + 1]; n += blockDim.x) op(n);
+    __syncthreads();
   }
-  if (MODE == kTreeFactor) {
-    for (int i = tid; i < nn; i += nth) { S.a[i] = t.diag0[b0 + i]; S.b[i] = t.tg[b0 + i]; }
-  } else if (MODE == kTreeUp) {
-    for (int i = tid; i < nn; i += nth) {
-      S.a[i] = t.r[b0 + i];
-      S.c[i] = t.gd[b0 + i];
-      if (top) { S.b[i] = t.d[b0 + i]; S.par[i] = t.t_parent[b0 + i]; }
-    }
-  } else {
-    for (int i = tid; i < nn; i += nth) {
-      S.a[i] = t.r[b0 + i];
-      S.b[i] = t.d[b0 + i];
-      S.c[i] = t.gd[b0 + i];
-      S.par[i] = t.t_parent[b0 + i];
+  if (tid < 32) {
+    for (int L = min(ci.Lw, ci.nl - 1); L >= 0; --L) {
+      for (int n = S.lvl[L] + tid; n < S.lvl[L + 1]; n += 32) op(n);
+      __syncwarp();
     }
   }
   __syncthreads();
-  if (MODE != kTreeDown) {
-    if (top) {
-      // children that live in bottom chunks were finished by other blocks of this launch:
-      // read them through L2 (__ldcg), fold them in before the on-chip level loop
-      for (int i = tid; i < nn; i += nth) {
-        double acc = S.a[i];
-        for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
-          const int c = S.cidx[k];
-          if (c < b0) {
-            if (MODE == kTreeFactor) acc -= t.tg[c] * __ldcg(t.gd + c);
-            else acc += t.gd[c] * __ldcg(t.r + c);
-          }
-        }
-        S.a[i] = acc;
-      }
-      __syncthreads();
-    }
-    for (int L = nl - 1; L >= 0; --L) {
-      for (int n = S.lvl[L] + tid; n < S.lvl[L + 1]; n += nth) {
-        const int i = n - b0;
-        double acc = S.a[i];
-        for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
-          const int c = S.cidx[k] - b0;
-          if (c >= 0) {
-            if (MODE == kTreeFactor) acc -= S.b[c] * S.c[c];
-            else acc += S.c[c] * S.a[c];
-          }
-        }
-        S.a[i] = acc;
-        if (MODE == kTreeFactor) S.c[i] = S.b[i] / acc;
-      }
-      __syncthreads();
-    }
-    if (MODE == kTreeFactor) {
-      for (int i = tid; i < nn; i += nth) { t.d[b0 + i] = S.a[i]; t.gd[b0 + i] = S.c[i]; }
-    } else if (!top) {
-      for (int i = tid; i < nn; i += nth) t.r[b0 + i] = S.a[i];
+}
+
+// root -> leaf
+template <typename NodeOp>
+__device__ __forceinline__ void sweep_down(const TreeSmem& S, const ChunkInfo& ci, NodeOp op) {
+  const int tid = threadIdx.x;
+  if (tid < 32) {
+    for (int L = 0; L <= min(ci.Lw, ci.nl - 1); ++L) {
+      for (int n = S.lvl[L] + tid; n < S.lvl[L + 1]; n += 32) op(n);
+      __syncwarp();
     }
   }
-  if (MODE == kTreeDown || (MODE == kTreeUp && top)) {
-    // back-substitution, shallowest level first: lam = r/d + gd * lam(parent)
-    for (int L = 0; L < nl; ++L) {
-      for (int n = S.lvl[L] + tid; n < S.lvl[L + 1]; n += nth) {
-        const int i = n - b0;
-        const int p = S.par[i];
-        double v = S.a[i] / S.b[i];
-        if (p >= b0 && p < b1) v += S.c[i] * S.a[p - b0];
-        else if (p >= 0) v += S.c[i] * t.lam[p];
-        S.a[i] = v;
-      }
-      __syncthreads();
-    }
-    for (int i = tid; i < nn; i += nth) {
-      t.lam[b0 + i] = S.a[i];
-      t.lam_nat[t.bif_of_t[b0 + i]] = S.a[i];
-    }
+  __syncthreads();
+  for (int L = ci.Lw + 1; L < ci.nl; ++L) {
+    for (int n = S.lvl[L] + tid; n < S.lvl[L + 1]; n += blockDim.x) op(n);
+    __syncthreads();
   }
 }
 
-// grid = max(n_bottom, 1); MODE kTreeFactor / kTreeUp run the top chunk in the last block.
-template <int MODE>
-__global__ void __launch_bounds__(1024)
-tree_fused_kernel(TreeDev t, int n_bottom, unsigned int* ticket) {
+__device__ __forceinline__ void load_children(const TreeDev& t, const ChunkInfo& ci, TreeSmem& S) {
+  const int nn = ci.b1 - ci.b0;
+  for (int i = threadIdx.x; i <= nn; i += blockDim.x) S.cptr[i] = t.t_cptr[ci.b0 + i] - ci.cb;
+  for (int i = threadIdx.x; i < ci.ce - ci.cb; i += blockDim.x) S.cidx[i] = t.t_cidx[ci.cb + i];
+}
+
+// numeric factorisation of one chunk: d_n = diag0_n - sum_c tg_c * gd_c, gd_n = tg_n / d_n;
+// t.d receives 1/d.  `top`: children below b0 live in bottom chunks (already written to HBM).
+__device__ __forceinline__ void factor_chunk(const TreeDev& t, TreeSmem& S, int chunk, bool top) {
+  const ChunkInfo ci = load_chunk_info(t, chunk, S);
+  const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
+  load_children(t, ci, S);
+  for (int i = tid; i < nn; i += nth) { S.a[i] = t.diag0[b0 + i]; S.b[i] = t.tg[b0 + i]; }
+  __syncthreads();
+  if (top) {
+    for (int i = tid; i < nn; i += nth) {
+      double acc = S.a[i];
+      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+        const int c = S.cidx[k];
+        if (c < b0) acc -= t.tg[c] * __ldcg(t.gd + c);
+      }
+      S.a[i] = acc;
+    }
+    __syncthreads();
+  }
+  sweep_up(S, ci, [&](int n) {
+    const int i = n - b0;
+    double acc = S.a[i];
+    for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+      const int c = S.cidx[k] - b0;
+      if (c >= 0) acc -= S.b[c] * S.c[c];
+    }
+    const double inv = 1.0 / acc;
+    S.a[i] = inv;
+    S.c[i] = S.b[i] * inv;
+  });
+  for (int i = tid; i < nn; i += nth) { t.d[b0 + i] = S.a[i]; t.gd[b0 + i] = S.c[i]; }
+}
+
+// stage a chunk for the solve: a = r, b = 1/d, c = gd, par
+__device__ __forceinline__ void load_solve_chunk(const TreeDev& t, const ChunkInfo& ci, TreeSmem& S) {
+  const int nn = ci.b1 - ci.b0;
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+    S.a[i] = t.r[ci.b0 + i];
+    S.b[i] = t.d[ci.b0 + i];
+    S.c[i] = t.gd[ci.b0 + i];
+    S.par[i] = t.t_parent[ci.b0 + i];
+  }
+}
+
+__device__ __forceinline__ void solve_up(const TreeDev& t, TreeSmem& S, const ChunkInfo& ci, bool top) {
+  const int b0 = ci.b0, nn = ci.b1 - ci.b0;
+  if (top) {
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+      double acc = S.a[i];
+      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+        const int c = S.cidx[k];
+        if (c < b0) acc += t.gd[c] * __ldcg(t.r + c);
+      }
+      S.a[i] = acc;
+    }
+    __syncthreads();
+  }
+  sweep_up(S, ci, [&](int n) {
+    const int i = n - b0;
+    double acc = S.a[i];
+    for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+      const int c = S.cidx[k] - b0;
+      if (c >= 0) acc += S.c[c] * S.a[c];
+    }
+    S.a[i] = acc;
+  });
+}
+
+// lam = r/d + gd * lam(parent); parents outside the chunk (top chunk) are read through L2
+__device__ __forceinline__ void solve_down(const TreeDev& t, TreeSmem& S, const ChunkInfo& ci) {
+  const int b0 = ci.b0, b1 = ci.b1, nn = ci.b1 - ci.b0;
+  sweep_down(S, ci, [&](int n) {
+    const int i = n - b0;
+    const int p = S.par[i];
+    double v = S.a[i] * S.b[i];
+    if (p >= b0 && p < b1) v += S.c[i] * S.a[p - b0];
+    else if (p >= 0) v += S.c[i] * __ldcg(t.lam + p);
+    S.a[i] = v;
+  });
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+    t.lam[b0 + i] = S.a[i];
+    t.lam_nat[t.bif_of_t[b0 + i]] = S.a[i];
+  }
+}
+
+// true in the block that finished last
+__device__ __forceinline__ bool last_block_done(TreeSmem& S, unsigned int* ticket, int n_bottom) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) S.last = (atomicAdd(ticket, 1u) == (unsigned int)n_bottom - 1);
+  __syncthreads();
+  if (S.last) __threadfence();
+  return S.last;
+}
+
+// grid = max(n_bottom, 1)
+__global__ void __launch_bounds__(kTreeThreads)
+tree_factor_kernel(TreeDev t, int n_bottom, unsigned int* ticket) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
   TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
-  if (n_bottom > 0) tree_chunk<MODE>(t, S, blockIdx.x, false);
-  if (MODE == kTreeDown) return;
   if (n_bottom > 0) {
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) S.last = (atomicAdd(ticket, 1u) == (unsigned int)n_bottom - 1);
-    __syncthreads();
-    if (!S.last) return;
-    __threadfence();
+    factor_chunk(t, S, blockIdx.x, false);
+    if (!last_block_done(S, ticket, n_bottom)) return;
   }
-  tree_chunk<MODE>(t, S, n_bottom, true);
+  factor_chunk(t, S, n_bottom, true);
   if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// MODE kTreeUp: forward sweep of the bottom chunks, top chunk (forward + backward) in the last
+// block.  MODE kTreeDown: backward sweep of the bottom chunks.  (two-launch path)
+template <int MODE>
+__global__ void __launch_bounds__(kTreeThreads)
+tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket) {
+  extern __shared__ __align__(16) unsigned char tree_smem_raw[];
+  TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
+  if (MODE == kTreeDown) {
+    const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
+    load_solve_chunk(t, ci, S);
+    __syncthreads();
+    solve_down(t, S, ci);
+    return;
+  }
+  if (n_bottom > 0) {
+    const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
+    load_children(t, ci, S);
+    load_solve_chunk(t, ci, S);
+    __syncthreads();
+    solve_up(t, S, ci, false);
+    for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x) t.r[ci.b0 + i] = S.a[i];
+    if (!last_block_done(S, ticket, n_bottom)) return;
+  }
+  const ChunkInfo ti = load_chunk_info(t, n_bottom, S);
+  load_children(t, ti, S);
+  load_solve_chunk(t, ti, S);
+  __syncthreads();
+  solve_up(t, S, ti, true);
+  solve_down(t, S, ti);
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// single-launch solve: requires all n_bottom blocks to be co-resident (cooperative launch)
+__global__ void __launch_bounds__(kTreeThreads)
+tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch) {
+  extern __shared__ __align__(16) unsigned char tree_smem_raw[];
+  TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
+  const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
+  load_children(t, ci, S);
+  load_solve_chunk(t, ci, S);
+  __syncthreads();
+  solve_up(t, S, ci, false);
+  // publish the chunk roots (the shallowest levels may hold several subtree roots: publish the
+  // whole chunk only in the block that will recycle its staging buffer)
+  for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x)
+    if (S.par[i] < ci.b0 || S.par[i] >= ci.b1) t.r[ci.b0 + i] = S.a[i];
+  if (last_block_done(S, ticket, n_bottom)) {
+    // park this block's chunk, solve the top chunk in the same buffer, reload
+    for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x) t.r[ci.b0 + i] = S.a[i];
+    __syncthreads();
+    const ChunkInfo ti = load_chunk_info(t, n_bottom, S);
+    load_children(t, ti, S);
+    load_solve_chunk(t, ti, S);
+    __syncthreads();
+    solve_up(t, S, ti, true);
+    solve_down(t, S, ti);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *ticket = 0u;
+      __threadfence();
+      atomicExch(flag, epoch);
+    }
+    load_chunk_info(t, blockIdx.x, S);
+    load_solve_chunk(t, ci, S);
+    __syncthreads();
+  } else {
+    if (threadIdx.x == 0) {
+      while (atomicAdd(flag, 0u) != epoch) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  solve_down(t, S, ci);
 }
 
 // Edge condensation: c_e = sum r_q - w.F,  F_N = sum r_p
