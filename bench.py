@@ -240,6 +240,14 @@ def run_gpu(args):
     t_pc = time_kernel(dev, lambda: dev.call("nxfx_pc_apply", solver.b.d.c_ptr, yv.d.c_ptr), reps)
     gbs_spmv = bytes_spmv / (t_spmv * 1e-3) / 1e9
     gbs_asm = bytes_asm / (t_asm * 1e-3) / 1e9
+    traffic = {"spmv": None, "assembly": None, "spmv_note": None}
+    try:  # DRAM bytes per launch from the committed ncu --set full capture of this workload
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
+            tj = json.load(fh)
+        if tj["n_dofs"] == n_dofs:
+            traffic = {"spmv": tj["spmv"]["bytes"], "assembly": tj["assembly"]["bytes"], "spmv_note": tj["spmv"]["kernel"]}
+    except (OSError, KeyError, ValueError):
+        pass
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -257,10 +265,10 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "spmv_pipe_kernel<0> (CSR SpMV, TMA bulk pipeline)", "bound": "hbm", "achieved": gbs_spmv, "peak": peak,
-                     "peak_kind": peak_kind, "unit": "GB/s", "frac": gbs_spmv / peak, "traffic": None,
-                     "algorithmic_bytes": bytes_spmv, "ms": t_spmv},
+                     "peak_kind": peak_kind, "unit": "GB/s", "frac": gbs_spmv / peak, "traffic": traffic["spmv"],
+                     "traffic_kernel": traffic["spmv_note"], "algorithmic_bytes": bytes_spmv, "ms": t_spmv},
         "roofline_assembly": {"kernel": "assemble_tiles_kernel<false,true> (matrix + rhs, one launch)", "bound": "hbm", "achieved": gbs_asm, "peak": peak,
-                              "peak_kind": peak_kind, "unit": "GB/s", "frac": gbs_asm / peak, "traffic": None,
+                              "peak_kind": peak_kind, "unit": "GB/s", "frac": gbs_asm / peak, "traffic": traffic["assembly"],
                               "algorithmic_bytes": bytes_asm, "ms": t_asm},
         "kernel_ms": {"assemble": t_asm, "spmv": t_spmv, "pc_apply": t_pc, "pc_setup": t_pcs},
     }

@@ -219,3 +219,49 @@ def test_accumulate_semantics_and_errors():
     solver.assemble()
     with pytest.raises(RuntimeError, match="did not converge"):
         solver.solve()
+
+
+def test_full_size_properties():
+    """BASELINE headline size (make_tree(20,20,20), N=1, 3,670,012 DOFs): size-independent
+    properties instead of an element-wise oracle comparison -- nnz formula, pattern symmetry of
+    the coupling blocks, true residual, Kirchhoff at every bifurcation, q constant per edge,
+    the DG0 pressure recurrence, and the resistor-network closed form."""
+    import scipy.sparse as sp
+
+    n = 20
+    G = ng.make_tree(n, n, n, as_arrays=True)
+    nm = nxfx.NetworkMesh(G, N=1, color_strategy="smallest_last")
+    asm = nxfx.HydraulicNetworkAssembler(nm)
+    asm.compute_forms(p_bc_ex=P_Y)
+    solver = nxfx.Solver(asm, petsc_options={"ksp_type": "preonly", "pc_type": "lu", "nxfx_final_residual": True,
+                                             "ksp_error_if_not_converged": True})
+    solver.assemble()
+    sol = solver.solve()
+    E = G.number_of_edges()
+    n_bif = nm.bifurcation_values.size
+    assert asm.num_dofs == 3670012 and solver.A.nnz == 14680044 == E * 8 + 4 * (2 * E - nm.boundary_values.size)
+    assert solver.info.residual_norm <= 1e-13 * solver.info.rhs_norm
+    rp_, ci, va = solver.A.getValuesCSR()
+    A = sp.csr_matrix((va, ci, rp_), shape=(asm.num_dofs,) * 2)
+    x = np.concatenate([f.x.array for f in sol])
+    b = solver.b.array_r
+    assert np.linalg.norm(A @ x - b) <= 1e-13 * np.linalg.norm(b)
+    nq, nc = 2 * E, E
+    lam_rows = A[nq + nc:]
+    assert np.abs(lam_rows @ x).max() < 1e-12  # flux conservation at every bifurcation
+    # the multiplier blocks are transposes of each other, the pressure blocks negative transposes
+    assert abs(A[nq + nc:, :nq] - A[:nq, nq + nc:].T).max() == 0.0
+    assert abs(A[nq:nq + nc, :nq] + A[:nq, nq:nq + nc].T).max() == 0.0
+    fb = 2 * nm.edge_slot.astype(np.int64)
+    q0, q1 = x[fb], x[fb + 1]
+    np.testing.assert_allclose(q0, q1, rtol=1e-9, atol=1e-13)  # f = 0: q constant along an edge
+    # closed form: resistor network with boundary pressures -p_bc (SURVEY A.3)
+    net = helpers.oracle_for(nm, 1)
+    q_edge, lam = net.resistor_network_solution(net.eval_pbc(P_Y))
+    assert helpers.rel_l2(x[nq + nc:], lam) < 1e-9
+    assert helpers.rel_l2(q0, q_edge) < 1e-9
+    # DG0 pressure of the single cell: p = lambda_u - R q h / 2 (inlet edge: -p_bc(x_u) - ...)
+    h = net.cell_lengths()
+    lu = net.lm_index[net.edges[:, 0]]
+    pu = np.where(lu >= 0, lam[np.maximum(lu, 0)], -net.eval_pbc(P_Y)[net.edges[:, 0]])
+    np.testing.assert_allclose(x[nq:nq + nc], pu - q_edge * h / 2, rtol=1e-8, atol=1e-11)
