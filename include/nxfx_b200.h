@@ -182,6 +182,33 @@ int nxfx_assemble_solve_host(nxfx_ctx* ctx, const double* node_pos_h, const doub
                              double R_const, double f_const, const nxfx_solve_opts* opts,
                              double* x_h, nxfx_solve_info* info);
 
+/* ---- (6) multi-GPU: one rank's part of a partitioned network ------------------------------------ *
+ * Replaces what MPI does inside DOLFINx/PETSc/MUMPS at assembly.py:355-367 and solver.py:127-132
+ * (stash exchange, ghost updates, distributed LU).  The ctx holds one rank's sub-network in which
+ * the multipliers of the cut bifurcations are REPLICATED (see networks_fenicsx_b200/distributed.py).
+ * Every quantity that couples ranks is additive; the caller all-reduces (SUM) the small buffers
+ * between the begin/end halves with its own communicator (torch.distributed / NCCL):
+ *   shared_lm_h [n_shared]   local multiplier indices of the replicated multipliers
+ *   lam_weight_h [n_bif]     1 where this rank counts the multiplier row (norms, -r_lambda), else 0
+ *   buf_d                    caller-owned device buffer, 2*n_top doubles (nxfx_top_size)
+ *   nxfx_pc_setup_begin  -> buf = [partial pivots | link conductances] of the top chunk
+ *   nxfx_pc_setup_end    <- all-reduced buf: factorises the top chunk (identically on all ranks)
+ *   nxfx_pc_apply_begin  -> buf[0:n_top] = partial right-hand side of the top chunk
+ *   nxfx_pc_apply_end    <- all-reduced buf: top solve, back-substitution; z = or += P^{-1} r
+ *   nxfx_pack_shared / nxfx_unpack_shared  shared multiplier rows of a vector <-> buf (after
+ *                        y = A x these rows are partial sums)
+ *   nxfx_norm2_owned     out_d[0] = sum of squares over the entries this rank owns (async)     */
+int nxfx_set_shared(nxfx_ctx* ctx, int32_t n_shared, const int32_t* shared_lm_h,
+                    const double* lam_weight_h);
+int nxfx_top_size(nxfx_ctx* ctx, int32_t* n_top);
+int nxfx_pc_setup_begin(nxfx_ctx* ctx, double* buf_d);
+int nxfx_pc_setup_end(nxfx_ctx* ctx, double* buf_d);
+int nxfx_pc_apply_begin(nxfx_ctx* ctx, const double* r_d, double* buf_d);
+int nxfx_pc_apply_end(nxfx_ctx* ctx, const double* r_d, double* z_d, double* buf_d, int add);
+int nxfx_pack_shared(nxfx_ctx* ctx, const double* v_d, double* buf_d);
+int nxfx_unpack_shared(nxfx_ctx* ctx, const double* buf_d, double* v_d);
+int nxfx_norm2_owned(nxfx_ctx* ctx, const double* v_d, double* out_d);
+
 /* ---- post-processing ----------------------------------------------------------------------- *
  * Replaces Function.interpolate into the DG space in extract_global_flux: post_processing.py:36-51.
  * out_d [2*n_cells]: DG1 dofs (cell-wise [q(first vertex), q(second vertex)]).                       */

@@ -103,6 +103,15 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.POINTER(SolveOpts),
          C.c_void_p, C.POINTER(SolveInfo)],
     ),
+    "nxfx_set_shared": (C.c_int, [C.c_void_p, C.c_int32, c_i32p, c_f64p]),
+    "nxfx_top_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "nxfx_pc_setup_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nxfx_pc_setup_end": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nxfx_pc_apply_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nxfx_pc_apply_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "nxfx_pack_shared": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nxfx_unpack_shared": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nxfx_norm2_owned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nxfx_global_flux": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

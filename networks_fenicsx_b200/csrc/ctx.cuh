@@ -38,7 +38,7 @@ struct DevBuf {
 
 struct TreeSchedule {
   bool set = false;
-  int n_chunks = 0, n_lvl_ptr = 0, n_chords = 0;
+  int n_chunks = 0, n_lvl_ptr = 0, n_chords = 0, n_top = 0;
   DevBuf<int32_t> bif_of_t, chunk_desc;
   DevBuf<double> lam_nat;
   DevBuf<int32_t> t_of_bif, t_parent, t_pedge, t_cptr, t_cidx, chunk_lptr, lvl_ptr, chord_edge;
@@ -80,6 +80,10 @@ struct nxfx_ctx {
   nxfx::DevBuf<double> scal;                     // device scalars / partials
   nxfx::DevBuf<unsigned int> ticket;  // [0] reductions, [1] tree sweeps, [2] tree epoch flag
   double* scal_h = nullptr;  // pinned mirror
+  // multi-GPU: replicated multipliers
+  int32_t n_shared = 0;
+  nxfx::DevBuf<int32_t> shared_lm;
+  nxfx::DevBuf<double> lam_weight;
   // e2e staging
   nxfx::DevBuf<double> e2e_pbc, e2e_b, e2e_x;
 };

@@ -199,7 +199,7 @@ int tree_pass(nxfx_ctx* ctx, bool factor) {
     const int grid = std::max(nb, 1);
     unsigned int* tk = ctx->ticket.p + 1;
     if (factor) {
-      NXFX_LAUNCH(ctx, tree_factor_kernel, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk);
+      NXFX_LAUNCH(ctx, tree_factor_kernel, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1);
     } else if (s.coop_ok && nb > 0) {
       unsigned int* fl = ctx->ticket.p + 2;
       unsigned int ep = ++s.epoch;
@@ -209,8 +209,8 @@ int tree_pass(nxfx_ctx* ctx, bool factor) {
                                                  args, sizeof(TreeSmem), ctx->stream));
       ctx->launches++;
     } else {
-      NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk);
-      if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, tk);
+      NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1);
+      if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1);
     }
     return NXFX_OK;
   }
@@ -266,7 +266,7 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
               r, ctx->edge_c.p, ctx->edge_fn.p);
   if (ctx->n_bif > 0) {
     NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r,
-                ctx->edge_g.p, ctx->edge_c.p, ctx->edge_fn.p);
+                ctx->edge_g.p, ctx->edge_c.p, ctx->edge_fn.p, ctx->lam_weight.p);
     int rc = tree_pass(ctx, false);
     if (rc) return rc;
   }
@@ -551,6 +551,9 @@ int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gd
     if ((bif_inc[k] >> 1) < 0 || (bif_inc[k] >> 1) >= E)
       return fail(ctx, NXFX_ERR_INVALID, "bif_inc[%d] out of range", k);
   ctx->has_network = ctx->has_pattern = ctx->has_pbc = ctx->assembled = ctx->pc_ready = false;
+  ctx->n_shared = 0;
+  ctx->shared_lm.release();
+  ctx->lam_weight.release();
   ctx->tree.set = false;
   ctx->n_nodes = n_nodes; ctx->E = n_edges; ctx->gdim = gdim; ctx->N = N; ctx->n_bif = n_bif;
   ctx->n_inc = n_inc; ctx->nv = nv; ctx->nc = nc; ctx->nq = nq; ctx->poff = nq; ctx->loff = nq + nc;
@@ -707,7 +710,8 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
   NXFX_REQUIRE(ctx, chunk_lptr[0] == 0 && chunk_lptr[n_chunks] == n_lvl_ptr - 1 && lvl_ptr[0] == 0 &&
                         lvl_ptr[n_lvl_ptr - 1] == ctx->n_bif, "inconsistent level tables");
   for (size_t t = 0; t < nb; ++t) {
-    if (t_parent[t] >= (int32_t)nb || t_pedge[t] >= ctx->E || (t_parent[t] >= 0) != (t_pedge[t] >= 0))
+    // (a parent without a local link edge is legal: multi-GPU, the link belongs to another rank)
+    if (t_parent[t] >= (int32_t)nb || t_pedge[t] >= ctx->E || (t_pedge[t] >= 0 && t_parent[t] < 0))
       return fail(ctx, NXFX_ERR_INVALID, "tree schedule: bad parent at %zu", t);
   }
   int rc;
@@ -727,6 +731,7 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
   if ((rc = upload(ctx, s.lvl_ptr, lvl_ptr, (size_t)n_lvl_ptr))) return rc;
   if ((rc = upload(ctx, s.chord_edge, chord_edge, (size_t)std::max(0, n_chords)))) return rc;
   s.n_chunks = n_chunks; s.n_lvl_ptr = n_lvl_ptr; s.n_chords = n_chords;
+  s.n_top = lvl_ptr[chunk_lptr[n_chunks]] - lvl_ptr[chunk_lptr[n_chunks - 1]];
   // shared-memory sweeps need every chunk (nodes, levels) to fit the on-chip tables
   s.fast_ok = true;
   for (int c = 0; c < n_chunks; ++c) {
@@ -756,6 +761,10 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
       s.coop_ok = (n_chunks - 1) <= per_sm * ctx->sm_count;
     cudaGetLastError();
     NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<true, kPartial>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<true, kFinish>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<false, kPartial>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<false, kFinish>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
     NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_solve_kernel<kTreeUp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
     NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_solve_kernel<kTreeDown>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
   }
@@ -837,6 +846,117 @@ int nxfx_assemble_solve_host(nxfx_ctx* ctx, const double* node_pos, const double
   if ((rc = nxfx_solve(ctx, ctx->e2e_b.p, ctx->e2e_x.p, opts, info))) return rc;
   NXFX_CUDA(ctx, cudaMemcpyAsync(x_h, ctx->e2e_x.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NXFX_OK;
+}
+
+// ---- (6) multi-GPU: partitioned network ----------------------------------------------------------
+int nxfx_set_shared(nxfx_ctx* ctx, int32_t n_shared, const int32_t* shared_lm, const double* lam_weight) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_network, "no network");
+  NXFX_REQUIRE(ctx, n_shared >= 0 && n_shared <= ctx->n_bif && (n_shared == 0 || shared_lm) && lam_weight, "bad arguments");
+  for (int32_t i = 0; i < n_shared; ++i)
+    if (shared_lm[i] < 0 || shared_lm[i] >= ctx->n_bif) return fail(ctx, NXFX_ERR_INVALID, "shared_lm[%d] out of range", i);
+  int rc;
+  if ((rc = upload(ctx, ctx->shared_lm, shared_lm, (size_t)n_shared))) return rc;
+  if ((rc = upload(ctx, ctx->lam_weight, lam_weight, (size_t)ctx->n_bif))) return rc;
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->n_shared = n_shared;
+  return NXFX_OK;
+}
+
+static int dist_ready(nxfx_ctx* ctx, const double* buf) {
+  NXFX_REQUIRE(ctx, ctx->tree.set && ctx->tree.fast_ok && ctx->tree.n_chunks >= 1 && buf, "needs a shared-memory tree schedule and a buffer");
+  auto& s = ctx->tree;
+  const int top_nodes = s.n_lvl_ptr > 0 ? ctx->n_bif - 0 : 0;
+  (void)top_nodes;
+  return NXFX_OK;
+}
+
+int nxfx_top_size(nxfx_ctx* ctx, int32_t* n_top) {
+  if (!ctx || !n_top) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->tree.set && ctx->tree.n_chunks >= 1, "no tree schedule");
+  *n_top = ctx->tree.n_top;
+  return NXFX_OK;
+}
+
+int nxfx_pc_setup_begin(nxfx_ctx* ctx, double* buf) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  int rc = dist_ready(ctx, buf);
+  if (rc) return rc;
+  NXFX_REQUIRE(ctx, ctx->assembled, "assemble the matrix before pc_setup");
+  auto& s = ctx->tree;
+  TreeDev t = make_tree(ctx);
+  const int nb = s.n_chunks - 1;
+  NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N, ctx->cell_rh.p, ctx->edge_g.p);
+  NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx), t, ctx->edge_g.p);
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_factor_kernel, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
+  NXFX_LAUNCH(ctx, (tree_top_kernel<true, kPartial>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
+  return NXFX_OK;
+}
+
+int nxfx_pc_setup_end(nxfx_ctx* ctx, double* buf) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  int rc = dist_ready(ctx, buf);
+  if (rc) return rc;
+  NXFX_LAUNCH(ctx, (tree_top_kernel<true, kFinish>), 1, kTreeThreads, sizeof(TreeSmem), make_tree(ctx), ctx->tree.n_chunks - 1, buf);
+  ctx->pc_ready = true;
+  return NXFX_OK;
+}
+
+int nxfx_pc_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
+  if (!ctx || !r) return NXFX_ERR_INVALID;
+  int rc = dist_ready(ctx, buf);
+  if (rc) return rc;
+  NXFX_REQUIRE(ctx, ctx->pc_ready, "pc_setup has not been run");
+  Net g = make_net(ctx);
+  TreeDev t = make_tree(ctx);
+  const int nb = ctx->tree.n_chunks - 1;
+  NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p, r, ctx->edge_c.p, ctx->edge_fn.p);
+  NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->edge_g.p, ctx->edge_c.p,
+              ctx->edge_fn.p, ctx->lam_weight.p);
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
+  NXFX_LAUNCH(ctx, (tree_top_kernel<false, kPartial>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
+  return NXFX_OK;
+}
+
+int nxfx_pc_apply_end(nxfx_ctx* ctx, const double* r, double* z, double* buf, int add) {
+  if (!ctx || !r || !z) return NXFX_ERR_INVALID;
+  int rc = dist_ready(ctx, buf);
+  if (rc) return rc;
+  Net g = make_net(ctx);
+  TreeDev t = make_tree(ctx);
+  const int nb = ctx->tree.n_chunks - 1;
+  NXFX_LAUNCH(ctx, (tree_top_kernel<false, kFinish>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
+  const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
+  if (add)
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+  else
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+  return NXFX_OK;
+}
+
+int nxfx_pack_shared(nxfx_ctx* ctx, const double* v, double* buf) {
+  if (!ctx || !v || !buf) return NXFX_ERR_INVALID;
+  if (ctx->n_shared > 0)
+    NXFX_LAUNCH(ctx, pack_shared_kernel, (int)cdiv(ctx->n_shared, kThreads), kThreads, 0, ctx->n_shared, (int)ctx->loff,
+                ctx->shared_lm.p, v, buf);
+  return NXFX_OK;
+}
+
+int nxfx_unpack_shared(nxfx_ctx* ctx, const double* buf, double* v) {
+  if (!ctx || !v || !buf) return NXFX_ERR_INVALID;
+  if (ctx->n_shared > 0)
+    NXFX_LAUNCH(ctx, unpack_shared_kernel, (int)cdiv(ctx->n_shared, kThreads), kThreads, 0, ctx->n_shared, (int)ctx->loff,
+                ctx->shared_lm.p, buf, v);
+  return NXFX_OK;
+}
+
+int nxfx_norm2_owned(nxfx_ctx* ctx, const double* v, double* out_d) {
+  if (!ctx || !v || !out_d) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_network, "no network");
+  NXFX_LAUNCH(ctx, weighted_norm2_kernel, vec_grid(ctx, ctx->ndofs), kThreads, 0, (int)ctx->ndofs, (int)ctx->loff, v,
+              ctx->lam_weight.p, ctx->scal.p, ctx->ticket.p, out_d);
   return NXFX_OK;
 }
 

@@ -195,15 +195,26 @@ __device__ __forceinline__ void load_children(const TreeDev& t, const ChunkInfo&
   for (int i = threadIdx.x; i < ci.ce - ci.cb; i += blockDim.x) S.cidx[i] = t.t_cidx[ci.cb + i];
 }
 
+// Phases of the top chunk (multi-GPU): kPartial stops after folding in this rank's bottom-chunk
+// children and writes the partial sums to `buf` (all-reduced by the caller); kFinish starts from
+// the all-reduced buffer.  kFull = single GPU.
+enum { kFull = 0, kPartial = 1, kFinish = 2 };
+
 // numeric factorisation of one chunk: d_n = diag0_n - sum_c tg_c * gd_c, gd_n = tg_n / d_n;
 // t.d receives 1/d.  `top`: children below b0 live in bottom chunks (already written to HBM).
-__device__ __forceinline__ void factor_chunk(const TreeDev& t, TreeSmem& S, int chunk, bool top) {
+// buf (top chunk, kPartial/kFinish): [partial d | tg], 2*nn doubles.
+__device__ __forceinline__ void factor_chunk(const TreeDev& t, TreeSmem& S, int chunk, bool top,
+                                             int phase = kFull, double* buf = nullptr) {
   const ChunkInfo ci = load_chunk_info(t, chunk, S);
   const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
   load_children(t, ci, S);
-  for (int i = tid; i < nn; i += nth) { S.a[i] = t.diag0[b0 + i]; S.b[i] = t.tg[b0 + i]; }
+  if (phase == kFinish) {
+    for (int i = tid; i < nn; i += nth) { S.a[i] = buf[i]; S.b[i] = buf[nn + i]; }
+  } else {
+    for (int i = tid; i < nn; i += nth) { S.a[i] = t.diag0[b0 + i]; S.b[i] = t.tg[b0 + i]; }
+  }
   __syncthreads();
-  if (top) {
+  if (top && phase != kFinish) {
     for (int i = tid; i < nn; i += nth) {
       double acc = S.a[i];
       for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
@@ -214,6 +225,12 @@ __device__ __forceinline__ void factor_chunk(const TreeDev& t, TreeSmem& S, int 
     }
     __syncthreads();
   }
+  if (phase == kPartial) {
+    for (int i = tid; i < nn; i += nth) { buf[i] = S.a[i]; buf[nn + i] = S.b[i]; }
+    return;
+  }
+  if (phase == kFinish)
+    for (int i = tid; i < nn; i += nth) t.tg[b0 + i] = S.b[i];  // all-reduced link conductances
   sweep_up(S, ci, [&](int n) {
     const int i = n - b0;
     double acc = S.a[i];
@@ -239,9 +256,14 @@ __device__ __forceinline__ void load_solve_chunk(const TreeDev& t, const ChunkIn
   }
 }
 
-__device__ __forceinline__ void solve_up(const TreeDev& t, TreeSmem& S, const ChunkInfo& ci, bool top) {
+__device__ __forceinline__ void solve_up(const TreeDev& t, TreeSmem& S, const ChunkInfo& ci, bool top,
+                                         int phase = kFull, double* buf = nullptr) {
   const int b0 = ci.b0, nn = ci.b1 - ci.b0;
-  if (top) {
+  if (phase == kFinish) {
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) S.a[i] = buf[i];
+    __syncthreads();
+  }
+  if (top && phase != kFinish) {
     for (int i = threadIdx.x; i < nn; i += blockDim.x) {
       double acc = S.a[i];
       for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
@@ -251,6 +273,10 @@ __device__ __forceinline__ void solve_up(const TreeDev& t, TreeSmem& S, const Ch
       S.a[i] = acc;
     }
     __syncthreads();
+  }
+  if (phase == kPartial) {
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) buf[i] = S.a[i];
+    return;
   }
   sweep_up(S, ci, [&](int n) {
     const int i = n - b0;
@@ -290,24 +316,46 @@ __device__ __forceinline__ bool last_block_done(TreeSmem& S, unsigned int* ticke
   return S.last;
 }
 
-// grid = max(n_bottom, 1)
+// grid = max(n_bottom, 1); do_top = 0 (multi-GPU): bottom chunks only
 __global__ void __launch_bounds__(kTreeThreads)
-tree_factor_kernel(TreeDev t, int n_bottom, unsigned int* ticket) {
+tree_factor_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
   TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
   if (n_bottom > 0) {
     factor_chunk(t, S, blockIdx.x, false);
+    if (!do_top) return;
     if (!last_block_done(S, ticket, n_bottom)) return;
   }
+  if (!do_top) return;
   factor_chunk(t, S, n_bottom, true);
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // MODE kTreeUp: forward sweep of the bottom chunks, top chunk (forward + backward) in the last
 // block.  MODE kTreeDown: backward sweep of the bottom chunks.  (two-launch path)
+// Top chunk alone, in the phases of the multi-GPU path (one block).
+// FACTOR: kPartial writes [partial d | tg] to buf, kFinish factorises from the all-reduced buf.
+// SOLVE:  kPartial writes the partial right-hand side, kFinish solves (forward + backward).
+template <bool FACTOR, int PHASE>
+__global__ void __launch_bounds__(kTreeThreads)
+tree_top_kernel(TreeDev t, int top_chunk, double* buf) {
+  extern __shared__ __align__(16) unsigned char tree_smem_raw[];
+  TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
+  if (FACTOR) {
+    factor_chunk(t, S, top_chunk, true, PHASE, buf);
+  } else {
+    const ChunkInfo ti = load_chunk_info(t, top_chunk, S);
+    load_children(t, ti, S);
+    load_solve_chunk(t, ti, S);
+    __syncthreads();
+    solve_up(t, S, ti, true, PHASE, buf);
+    if (PHASE == kFinish) solve_down(t, S, ti);
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kTreeThreads)
-tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket) {
+tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
   TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
   if (MODE == kTreeDown) {
@@ -324,8 +372,10 @@ tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket) {
     __syncthreads();
     solve_up(t, S, ci, false);
     for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x) t.r[ci.b0 + i] = S.a[i];
+    if (!do_top) return;
     if (!last_block_done(S, ticket, n_bottom)) return;
   }
+  if (!do_top) return;
   const ChunkInfo ti = load_chunk_info(t, n_bottom, S);
   load_children(t, ti, S);
   load_solve_chunk(t, ti, S);
@@ -402,12 +452,15 @@ edge_condense_kernel(Net g, const double* __restrict__ cell_rh, const double* __
 }
 
 // rhs_b = -r_lam + sum_in (F_N + g c) - sum_out g c      (schedule order)
+// lam_weight (multi-GPU): 0 on the ranks that hold a replicated multiplier without owning it, so
+// that -r_lambda is counted once in the all-reduced right-hand side; null = all ones.
 __global__ void __launch_bounds__(kThreads)
 bif_rhs_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* __restrict__ edge_g,
-               const double* __restrict__ edge_c, const double* __restrict__ edge_fn) {
+               const double* __restrict__ edge_c, const double* __restrict__ edge_fn,
+               const double* __restrict__ lam_weight) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n_bif) return;
-  double s = -r[g.loff + i];
+  double s = lam_weight ? -lam_weight[i] * r[g.loff + i] : -r[g.loff + i];
   for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) {
     const int inc = g.bif_inc[k], e = inc >> 1;
     const double gc = edge_g[e] * edge_c[e];
@@ -456,6 +509,21 @@ edge_backsub_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh,
     qa = qn;
     hl = hr;
   }
+}
+
+// ---- multi-GPU helpers --------------------------------------------------------------------------
+// shared (replicated) multiplier rows of a vector <-> contiguous buffer for the all-reduce
+__global__ void __launch_bounds__(kThreads)
+pack_shared_kernel(int n_shared, int loff, const int32_t* __restrict__ shared_lm,
+                   const double* __restrict__ v, double* __restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_shared) buf[i] = v[loff + shared_lm[i]];
+}
+__global__ void __launch_bounds__(kThreads)
+unpack_shared_kernel(int n_shared, int loff, const int32_t* __restrict__ shared_lm,
+                     const double* __restrict__ buf, double* __restrict__ v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_shared) v[loff + shared_lm[i]] = buf[i];
 }
 
 // z = D^{-1} r on flux rows (D = diag of the mass block), identity elsewhere

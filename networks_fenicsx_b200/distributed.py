@@ -1,0 +1,241 @@
+"""Edge partition of ONE network over several GPUs (north_star "each GPU owns an edge
+partition; NCCL carries the bifurcation-node halo exchange and the all-reduces").
+
+Partition = the elimination schedule's own structure (``schedule.py``): the bottom chunks
+(complete subtrees) are dealt to the ranks in order, every graph edge follows its deeper
+bifurcation, and the multipliers of the top chunk -- the cut bifurcations -- are REPLICATED on all
+ranks.  Everything that couples ranks is additive and small (n_top doubles):
+
+* ``y = A x``: the shared multiplier rows are partial sums -> one all-reduce;
+* preconditioner: the top chunk's partial diagonal / right-hand side (contributions of each rank's
+  chunk roots and incident edges) -> one all-reduce, then every rank eliminates the identical top
+  chunk redundantly and back-substitutes its own chunks;
+* norms: owned entries only, one all-reduce of the scalars.
+
+Host code (NumPy) in this file; collectives through ``torch.distributed`` (NCCL on GPUs, gloo in
+the CPU tests).
+"""
+
+from __future__ import annotations
+
+import dataclasses
+
+import numpy as np
+
+from .network_generation import ArrayGraph
+from .schedule import CHUNK_NODES, TreeSchedule, assemble_schedule, assign_chunks, spanning_forest
+
+
+@dataclasses.dataclass
+class TreePartition:
+    rank: int
+    world: int
+    graph: ArrayGraph  # local sub-network (nodes: endpoints of the local edges + all cut nodes)
+    node_degree: np.ndarray  # GLOBAL degree of every local node
+    global_nodes: np.ndarray  # local node -> global node
+    global_edges: np.ndarray  # local edge -> global edge
+    global_bif: np.ndarray  # local multiplier -> global multiplier index
+    shared_lm: np.ndarray  # local multiplier indices of the replicated (top-chunk) multipliers
+    lam_weight: np.ndarray  # 1.0 where this rank counts the multiplier row in norms / -r_lambda
+    schedule: TreeSchedule  # local elimination schedule, top chunk (identical on all ranks) last
+    n_top: int
+    n_global_bif: int
+
+
+def partition_tree(graph: ArrayGraph, world: int, rank: int, chunk_nodes: int = CHUNK_NODES) -> TreePartition:
+    """Deterministic: every rank calls this with the same graph and gets its own part."""
+    edges = np.asarray(graph.edges, dtype=np.int64)
+    n_nodes = graph.number_of_nodes()
+    u, v = edges[:, 0], edges[:, 1]
+    deg_out = np.bincount(u, minlength=n_nodes)
+    deg_in = np.bincount(v, minlength=n_nodes)
+    degree = deg_in + deg_out
+    bif = np.flatnonzero(degree > 1)
+    n_bif = bif.size
+    lm = np.full(n_nodes, -1, dtype=np.int64)
+    lm[bif] = np.arange(n_bif)
+    inlets = np.flatnonzero((degree == 1) & (deg_out == 1))
+    parent, pedge, depth, chord = spanning_forest(edges, lm, n_bif, inlets)
+    if chord.size:
+        raise NotImplementedError("the multi-GPU partition needs a forest (no cycles among the bifurcations)")
+    cn = chunk_nodes
+    while True:
+        chunk, n_chunks = assign_chunks(parent, depth, cn)
+        if n_chunks - 1 >= world or cn <= 2:
+            break
+        cn //= 2
+    n_bottom = n_chunks - 1
+    if n_bottom < world:
+        raise ValueError(f"network too small to cut into {world} parts")
+    top = chunk == n_bottom
+    rank_of_chunk = (np.arange(n_bottom) * world) // n_bottom
+    owner_bif = np.where(top, 0, rank_of_chunk[np.minimum(chunk, n_bottom - 1)])  # top edges -> rank 0
+    # every edge follows its deeper bifurcation
+    a, b = lm[u], lm[v]
+    da = np.where(a >= 0, depth[np.maximum(a, 0)], -1)
+    db = np.where(b >= 0, depth[np.maximum(b, 0)], -1)
+    deeper = np.where(db >= da, b, a)
+    owner_edge = np.where(deeper >= 0, owner_bif[np.maximum(deeper, 0)], 0)
+    ge = np.flatnonzero(owner_edge == rank)
+    # local nodes: endpoints of the local edges and ALL cut (top-chunk) nodes, ascending global id
+    gn = np.unique(np.concatenate([edges[ge].ravel(), bif[top]]))
+    local_of = np.full(n_nodes, -1, dtype=np.int64)
+    local_of[gn] = np.arange(gn.size)
+    attrs = {k: np.asarray(val)[ge] for k, val in graph.edge_attrs.items()}
+    sub = ArrayGraph(np.asarray(graph.pos)[gn], local_of[edges[ge]], attrs)
+    # local multipliers (ascending global node id, as NetworkMesh numbers them)
+    lbif_nodes = gn[degree[gn] > 1]
+    gb = lm[lbif_nodes]  # global multiplier index of every local multiplier
+    lb_of_gb = np.full(n_bif, -1, dtype=np.int64)
+    lb_of_gb[gb] = np.arange(gb.size)
+    mine = top[gb] | (owner_bif[gb] == rank)
+    if not np.all(mine):
+        # a bifurcation of another rank's chunk can only appear here as the far end of one of our
+        # edges, which the "deeper bifurcation" rule excludes on forests
+        raise AssertionError("partition invariant violated")
+    lpar = np.where(parent[gb] >= 0, lb_of_gb[np.maximum(parent[gb], 0)], -1)
+    assert np.all((parent[gb] < 0) | (lpar >= 0)), "parent of a local multiplier is not local"
+    ledge_of = np.full(edges.shape[0], -1, dtype=np.int64)
+    ledge_of[ge] = np.arange(ge.size)
+    lpedge = np.where(pedge[gb] >= 0, ledge_of[np.maximum(pedge[gb], 0)], -1)
+    # my bottom chunks renumbered 0..k-1, the top chunk last
+    my_chunks = np.flatnonzero(rank_of_chunk == rank)
+    lchunk_of = np.full(n_chunks, -1, dtype=np.int64)
+    lchunk_of[my_chunks] = np.arange(my_chunks.size)
+    lchunk_of[n_bottom] = my_chunks.size
+    lchunk = lchunk_of[chunk[gb]]
+    assert np.all(lchunk >= 0)
+    sched = assemble_schedule(lpar, lpedge, depth[gb], lchunk, my_chunks.size + 1, np.zeros(0, dtype=np.int32))
+    shared = np.flatnonzero(top[gb])
+    weight = np.where(top[gb] & (rank != 0), 0.0, 1.0)
+    return TreePartition(rank, world, sub, degree[gn], gn, ge, gb, shared.astype(np.int32), weight, sched,
+                         int(top.sum()), n_bif)
+
+
+class DistributedSolver:
+    """Assemble + solve of ONE network cut over the ranks of ``torch.distributed`` (one process per
+    GPU).  Mirrors ``Solver`` for the default options (network-Schur direct solve + iterative
+    refinement); the collectives are three kinds of small SUM all-reduces (see module docstring).
+
+    Args:
+        graph: the GLOBAL network (every rank passes the same :class:`ArrayGraph`).
+        N: cells per graph edge.
+        p_bc_ex, f, R: as :meth:`HydraulicNetworkAssembler.compute_forms` (``R``/``f`` per-cell arrays
+            must already be restricted to the local edges).
+        device: CUDA ordinal of this rank.
+    """
+
+    def __init__(self, graph: ArrayGraph, N: int, p_bc_ex, f=None, R=None, device: int = 0,
+                 color_strategy="smallest_last", chunk_nodes: int = CHUNK_NODES, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        from .assembly import HydraulicNetworkAssembler
+        from .mesh import NetworkMesh
+        from .solver import Solver
+
+        self._C, self._torch, self._dist, self._group = C, torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.part = partition_tree(graph, self.world, self.rank, chunk_nodes)
+        part = self.part
+        self.mesh = NetworkMesh(part.graph, N=N, color_strategy=color_strategy, device=device,
+                                node_degree=part.node_degree)
+        assert np.array_equal(part.global_nodes[self.mesh.bifurcation_values], part.global_nodes[
+            np.flatnonzero(part.node_degree > 1)])
+        self.assembler = HydraulicNetworkAssembler(self.mesh)
+        self.assembler.compute_forms(p_bc_ex=p_bc_ex, f=f, R=R)
+        self.solver = Solver(self.assembler, schedule=part.schedule)
+        self.dev = self.mesh.device
+        shared = np.ascontiguousarray(part.shared_lm, dtype=np.int32)
+        weight = np.ascontiguousarray(part.lam_weight, dtype=np.float64)
+        self.dev.call("nxfx_set_shared", shared.size, _lib.as_i32p(shared), _lib.as_f64p(weight))
+        cuda = torch.device("cuda", device)
+        self._top = torch.zeros(2 * max(part.n_top, 1), dtype=torch.float64, device=cuda)
+        self._sh = torch.zeros(max(shared.size, 1), dtype=torch.float64, device=cuda)
+        self._nrm = torch.zeros(2 * 40, dtype=torch.float64, device=cuda)
+        self._r = self.dev.empty(self.assembler.num_dofs)
+        self.n_dofs_global = int(self._allreduce_scalar(self._owned_dofs()))
+        self.history: list[float] = []
+        self.rhs_norm = float("nan")
+
+    def _owned_dofs(self) -> int:
+        return int(self.assembler.num_dofs - self.part.n_top + (self.part.n_top if self.rank == 0 else 0))
+
+    def _allreduce_scalar(self, v: float) -> float:
+        t = self._torch.tensor([float(v)], dtype=self._torch.float64, device=self._top.device)
+        self._dist.all_reduce(t, group=self._group)
+        return float(t.item())
+
+    def _ptr(self, t, offset: int = 0):
+        return self._C.c_void_p(t.data_ptr() + 8 * offset)
+
+    def assemble(self) -> None:
+        self.solver.assemble()
+
+    def _apply(self, r_ptr, z_ptr, add: int) -> None:
+        top = self._ptr(self._top)
+        self.dev.call("nxfx_pc_apply_begin", r_ptr, top)
+        self._dist.all_reduce(self._top[: self.part.n_top], group=self._group)
+        self.dev.call("nxfx_pc_apply_end", r_ptr, z_ptr, top, add)
+
+    def solve(self, refine_steps: int = 1, final_residual: bool = False):
+        """x = P^{-1} b, then ``refine_steps`` refinement steps.  Returns the list of global
+        relative residual norms that were evaluated (the last one belongs to the iterate before the
+        last correction unless ``final_residual``)."""
+        dev, C = self.dev, self._C
+        b = self.solver.b.device_ptr()
+        x = self.solver.x.device_ptr_overwrite()
+        top = self._ptr(self._top)
+        dev.call("nxfx_pc_setup_begin", top)
+        self._dist.all_reduce(self._top, group=self._group)
+        dev.call("nxfx_pc_setup_end", top)
+        self._apply(b, x, 0)
+        n_eval = 0
+        for s in range(refine_steps + (1 if final_residual else 0)):
+            self._residual(b, x, n_eval)
+            n_eval += 1
+            if s < refine_steps:
+                self._apply(self._r.c_ptr, x, 1)
+        self.solver.x.mark_device_modified()
+        if n_eval:
+            self._dist.all_reduce(self._nrm[: 2 * n_eval], group=self._group)
+            vals = self._nrm[: 2 * n_eval].cpu().numpy()
+            self.rhs_norm = float(np.sqrt(vals[1]))
+            self.history = [float(np.sqrt(vals[2 * k]) / self.rhs_norm) for k in range(n_eval)]
+        else:
+            dev.sync()
+            self.history = []
+        return self.history
+
+    def _residual(self, b, x, k: int) -> None:
+        """r = b - A x with consistent shared rows; owned squared norms of r and b -> slot k."""
+        dev = self.dev
+        dev.call("nxfx_residual", b, x, self._r.c_ptr, None)
+        if self.part.shared_lm.size:
+            sh = self._ptr(self._sh)
+            dev.call("nxfx_pack_shared", self._r.c_ptr, sh)
+            self._dist.all_reduce(self._sh[: self.part.shared_lm.size], group=self._group)
+            dev.call("nxfx_unpack_shared", sh, self._r.c_ptr)
+        dev.call("nxfx_norm2_owned", self._r.c_ptr, self._ptr(self._nrm, 2 * k))
+        dev.call("nxfx_norm2_owned", b, self._ptr(self._nrm, 2 * k + 1))
+
+    # ---- results -------------------------------------------------------------------------------
+    def local_solution(self) -> np.ndarray:
+        return self.solver.x.array_r
+
+    def edge_values(self):
+        """(global edge ids, flux[E_loc, N+1], pressure[E_loc, N]) of the local edges and
+        (global multiplier ids, values) of the multipliers this rank owns."""
+        x = self.local_solution()
+        N = self.mesh.cells_per_edge
+        E = self.part.global_edges.size
+        fb = self.mesh.edge_slot.astype(np.int64) * (N + 1)
+        q = x[fb[:, None] + np.arange(N + 1)[None, :]]
+        nq = E * (N + 1)
+        p = x[nq: nq + E * N].reshape(E, N)
+        lam = x[nq + E * N:]
+        own = self.part.lam_weight > 0
+        return self.part.global_edges, q, p, self.part.global_bif[own], lam[own]

@@ -315,6 +315,9 @@ class NetworkMesh:
         comm: kept for signature compatibility (single process per GPU).
         graph_rank: kept for signature compatibility.
         device: CUDA device ordinal (extension; default 0).
+        node_degree: degree of every node in the GLOBAL graph when ``graph`` is one rank's part of
+            a partitioned network (extension, see ``distributed.py``): a cut bifurcation keeps its
+            multiplier although it may have a single local edge.
     """
 
     def __init__(
@@ -325,7 +328,9 @@ class NetworkMesh:
         comm=COMM_WORLD,
         graph_rank: int = 0,
         device: int | Device | None = None,
+        node_degree: npt.NDArray[np.integer] | None = None,
     ):
+        self._node_degree_override = node_degree
         self._comm = comm if comm is not None else COMM_WORLD
         self._device_arg = device
         self._dev: Device | None = None
@@ -379,6 +384,10 @@ class NetworkMesh:
         deg_in = np.bincount(v, minlength=n_nodes)
         deg_out = np.bincount(u, minlength=n_nodes)
         degree = deg_in + deg_out
+        if self._node_degree_override is not None:
+            degree = np.asarray(self._node_degree_override, dtype=np.int64)
+            if degree.shape != (n_nodes,) or np.any(degree < deg_in + deg_out):
+                raise ValueError("node_degree must give the global degree (>= local degree) of every node")
         self._degree = degree
         self._bifurcation_values = np.flatnonzero(degree > 1)
         self._boundary_values = np.flatnonzero(degree == 1)

@@ -37,15 +37,11 @@ class TreeSchedule:
         return self.chord_edge.size == 0
 
 
-def build_tree_schedule(edges: np.ndarray, node_lm: np.ndarray, n_bif: int,
-                        root_hint_nodes: np.ndarray | None = None,
-                        chunk_nodes: int = CHUNK_NODES) -> TreeSchedule:
-    """``edges[E,2]`` graph edges, ``node_lm[n_nodes]`` multiplier index or -1.
-    ``root_hint_nodes``: graph nodes (inlets) whose neighbouring bifurcations become roots."""
-    i32 = np.int32
-    if n_bif == 0:
-        z = np.zeros(0, dtype=i32)
-        return TreeSchedule(z, z, z, np.zeros(1, dtype=i32), z, np.zeros(1, dtype=i32), np.zeros(1, dtype=i32), z, z)
+def spanning_forest(edges: np.ndarray, node_lm: np.ndarray, n_bif: int,
+                    root_hint_nodes: np.ndarray | None = None):
+    """Level-synchronous BFS over the bifurcation graph.  Returns ``(parent, pedge, depth, chord)``:
+    parent bifurcation (-1 for roots), graph edge to the parent, depth, and the graph edges between
+    bifurcations that are not in the forest."""
     u, v = edges[:, 0], edges[:, 1]
     a, b = node_lm[u], node_lm[v]
     link = np.flatnonzero((a >= 0) & (b >= 0))
@@ -98,9 +94,15 @@ def build_tree_schedule(edges: np.ndarray, node_lm: np.ndarray, n_bif: int,
 
     tree_edge = np.zeros(edges.shape[0], dtype=bool)
     tree_edge[pedge[pedge >= 0]] = True
-    chord = link[~tree_edge[link]].astype(i32)
+    chord = link[~tree_edge[link]].astype(np.int32)
+    return parent, pedge, depth, chord
 
-    # subtree sizes, deepest level first
+
+def assign_chunks(parent: np.ndarray, depth: np.ndarray, chunk_nodes: int = CHUNK_NODES):
+    """Cut the forest into bottom chunks (bin-packed complete subtrees of <= ``chunk_nodes``
+    nodes) and one top chunk (the nodes whose subtree is larger).  Returns ``(chunk, n_chunks)``
+    with the top chunk last."""
+    n_bif = parent.size
     size = np.ones(n_bif, dtype=np.int64)
     by_depth = np.argsort(depth, kind="stable")
     dsorted = depth[by_depth]
@@ -110,36 +112,36 @@ def build_tree_schedule(edges: np.ndarray, node_lm: np.ndarray, n_bif: int,
         np.add.at(size, parent[lv], size[lv])
     heavy = size > chunk_nodes
     if not heavy.any():
-        chunk = np.zeros(n_bif, dtype=np.int64)  # everything in the single (top) chunk
-        n_chunks = 1
-    else:
-        # roots of the light subtrees hanging below heavy nodes (or light whole trees)
-        par_heavy = np.where(parent >= 0, heavy[np.maximum(parent, 0)], True)
-        croots = np.flatnonzero(~heavy & par_heavy)
-        # bin-pack consecutive subtree roots into chunks of <= chunk_nodes nodes
-        csz = size[croots]
-        cum = np.cumsum(csz)
-        bin_of_root = np.zeros(croots.size, dtype=np.int64)
-        start, base, k = 0, 0, 0
-        # greedy packing, vectorised by searchsorted jumps
-        while start < croots.size:
-            end = int(np.searchsorted(cum, base + chunk_nodes, side="right"))
-            end = max(end, start + 1)
-            bin_of_root[start:end] = k
-            base = cum[end - 1]
-            start = end
-            k += 1
-        n_bottom = k
-        chunk = np.full(n_bif, n_bottom, dtype=np.int64)  # heavy nodes -> top chunk (last)
-        chunk[croots] = bin_of_root
-        for lv in levels:  # propagate chunk ids root -> leaf
-            m = (~heavy[lv]) & (parent[lv] >= 0)
-            sel = lv[m]
-            inherit = ~heavy[parent[sel]]
-            chunk[sel[inherit]] = chunk[parent[sel[inherit]]]
-        n_chunks = n_bottom + 1
+        return np.zeros(n_bif, dtype=np.int64), 1  # everything in the single (top) chunk
+    # roots of the light subtrees hanging below heavy nodes (or light whole trees)
+    par_heavy = np.where(parent >= 0, heavy[np.maximum(parent, 0)], True)
+    croots = np.flatnonzero(~heavy & par_heavy)
+    # bin-pack consecutive subtree roots into chunks of <= chunk_nodes nodes
+    cum = np.cumsum(size[croots])
+    bin_of_root = np.zeros(croots.size, dtype=np.int64)
+    start, base, k = 0, 0, 0
+    while start < croots.size:
+        end = int(np.searchsorted(cum, base + chunk_nodes, side="right"))
+        end = max(end, start + 1)
+        bin_of_root[start:end] = k
+        base = cum[end - 1]
+        start = end
+        k += 1
+    n_bottom = k
+    chunk = np.full(n_bif, n_bottom, dtype=np.int64)  # heavy nodes -> top chunk (last)
+    chunk[croots] = bin_of_root
+    for lv in levels:  # propagate chunk ids root -> leaf
+        m = (~heavy[lv]) & (parent[lv] >= 0)
+        sel = lv[m]
+        inherit = ~heavy[parent[sel]]
+        chunk[sel[inherit]] = chunk[parent[sel[inherit]]]
+    return chunk, n_bottom + 1
 
-    # schedule order: by (chunk, depth), stable
+
+def assemble_schedule(parent, pedge, depth, chunk, n_chunks, chord) -> TreeSchedule:
+    """Order the nodes by (chunk, depth) and build the tables ``nxfx_set_tree_schedule`` takes."""
+    i32 = np.int32
+    n_bif = parent.size
     t_order = np.lexsort((depth, chunk))
     t_of_bif = np.empty(n_bif, dtype=np.int64)
     t_of_bif[t_order] = np.arange(n_bif)
@@ -155,5 +157,20 @@ def build_tree_schedule(edges: np.ndarray, node_lm: np.ndarray, n_bif: int,
     t_cptr = np.concatenate([[0], np.cumsum(np.bincount(t_parent[has_p], minlength=n_bif))])
     return TreeSchedule(
         t_of_bif.astype(i32), t_parent.astype(i32), t_pedge.astype(i32), t_cptr.astype(i32),
-        corder.astype(i32), chunk_lptr.astype(i32), lvl_ptr.astype(i32), chord, depth.astype(i32),
+        corder.astype(i32), chunk_lptr.astype(i32), lvl_ptr.astype(i32), np.asarray(chord, dtype=i32),
+        depth.astype(i32),
     )
+
+
+def build_tree_schedule(edges: np.ndarray, node_lm: np.ndarray, n_bif: int,
+                        root_hint_nodes: np.ndarray | None = None,
+                        chunk_nodes: int = CHUNK_NODES) -> TreeSchedule:
+    """``edges[E,2]`` graph edges, ``node_lm[n_nodes]`` multiplier index or -1.
+    ``root_hint_nodes``: graph nodes (inlets) whose neighbouring bifurcations become roots."""
+    i32 = np.int32
+    if n_bif == 0:
+        z = np.zeros(0, dtype=i32)
+        return TreeSchedule(z, z, z, np.zeros(1, dtype=i32), z, np.zeros(1, dtype=i32), np.zeros(1, dtype=i32), z, z)
+    parent, pedge, depth, chord = spanning_forest(edges, node_lm, n_bif, root_hint_nodes)
+    chunk, n_chunks = assign_chunks(parent, depth, chunk_nodes)
+    return assemble_schedule(parent, pedge, depth, chunk, n_chunks, chord)

@@ -40,6 +40,7 @@ class Solver:
         petsc_options_prefix: str = "NetworkSolver_",
         petsc_options: dict | None = None,
         kind: str | typing.Sequence[typing.Sequence[str]] | None = None,
+        schedule=None,
     ):
         self._assembler = assembler
         nm = assembler.network
@@ -64,7 +65,8 @@ class Solver:
             }
         self.ksp.options = dict(petsc_options)
         # elimination schedule of the bifurcation graph (the analysis phase of the direct solver)
-        self._schedule = build_tree_schedule(
+        # (``schedule``: a precomputed one, e.g. the local part of a partitioned network)
+        self._schedule = schedule if schedule is not None else build_tree_schedule(
             nm.graph_edges, nm.node_multiplier_index, nm.bifurcation_values.size,
             root_hint_nodes=nm._boundary_out_nodes,
         )

@@ -259,7 +259,9 @@ def graph_to_arrays(graph, coloring):
 class OracleNetwork:
     """Vectorised oracle of mesh arrays, dof tables, pattern, assembly and solve."""
 
-    def __init__(self, pos, edges, colors, N: int):
+    def __init__(self, pos, edges, colors, N: int, degree=None):
+        """``degree``: global node degrees when (pos, edges) is one part of a partitioned network
+        (test support for the multi-GPU partition; the reference has no such notion)."""
         pos = np.asarray(pos, dtype=np.float64)
         self.pos = pos
         self.edges = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
@@ -271,6 +273,8 @@ class OracleNetwork:
         u, v = self.edges[:, 0], self.edges[:, 1]
         # mesh.py:182-187
         self.degree = np.bincount(u, minlength=self.n_nodes) + np.bincount(v, minlength=self.n_nodes)
+        if degree is not None:
+            self.degree = np.asarray(degree)
         self.bifurcation_values = np.flatnonzero(self.degree > 1)
         self.boundary_values = np.flatnonzero(self.degree == 1)
         self.lm_index = np.full(self.n_nodes, -1, dtype=np.int64)
