@@ -100,28 +100,27 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_problem(n, device_index, rank=0, world=1):
+def build_problem(n, device_index):
     import networks_fenicsx_b200 as nxfx
 
     G = nxfx.network_generation.make_tree(n, n, n, as_arrays=True)
-    if world > 1:
-        # weak scaling: a forest of `world` n-generation trees, partitioned by connected component
-        # (zero-cut edge partition): every rank ends up owning exactly one tree
-        from networks_fenicsx_b200 import parallel
-
-        trees = []
-        for k in range(world):
-            t = nxfx.network_generation.ArrayGraph(G.pos.copy(), G.edges)
-            t.pos[:, 0] += 2.0 * n * k
-            trees.append(t)
-        F = parallel.forest(trees)
-        rank_of_edge = parallel.partition_components(F.edges, F.number_of_nodes(), world)
-        G = parallel.local_part(F, rank_of_edge, rank).graph
     nm = nxfx.NetworkMesh(G, N=1, color_strategy="smallest_last", device=device_index)
     asm = nxfx.HydraulicNetworkAssembler(nm, flux_degree=1, pressure_degree=0)
     asm.compute_forms(p_bc_ex=p_bc)
     solver = nxfx.Solver(asm)
     return nxfx, nm, asm, solver
+
+
+def build_distributed(n, device_index):
+    """N > 1: ONE n-generation tree cut over the ranks (distributed.py): every rank owns a set of
+    subtrees, the multipliers of the cut bifurcations are replicated, three kinds of small
+    all-reduces per solve."""
+    import networks_fenicsx_b200 as nxfx
+    from networks_fenicsx_b200.distributed import DistributedSolver
+
+    G = nxfx.network_generation.make_tree(n, n, n, as_arrays=True)
+    ds = DistributedSolver(G, 1, p_bc, device=device_index)
+    return nxfx, ds
 
 
 def time_kernel(dev, fn, reps):
@@ -152,11 +151,24 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n = args.generations
-    nxfx, nm, asm, solver = build_problem(n, local_rank, rank, world)
+    ds = None
+    if world > 1:
+        # weak scaling keeps ~one 20-generation subtree per GPU: n + log2(world) generations
+        if args.scaling == "weak":
+            n = args.generations + max(0, (world - 1).bit_length())
+        nxfx, ds = build_distributed(n, local_rank)
+        nm, asm, solver = ds.mesh, ds.assembler, ds.solver
+        ds.assemble()
+        ds.solve()
+        functions = None
+        n_dofs_total = ds.n_dofs_global
+    else:
+        nxfx, nm, asm, solver = build_problem(n, local_rank)
+        solver.assemble()
+        functions = solver.solve()  # also allocates the pinned result functions
+        n_dofs_total = asm.num_dofs
     dev = nm.device
     n_dofs = asm.num_dofs
-    solver.assemble()
-    functions = solver.solve()  # also allocates the pinned result functions
     nnz = solver.A.nnz
     E = nm.graph_edges.shape[0]
     nv = nm.mesh.topology.index_map(0).size_local
@@ -169,6 +181,10 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def step_resident():
+        if ds is not None:
+            ds.assemble()
+            ds.solve()
+            return
         solver.assemble()
         dev.call("nxfx_solve", solver.b.device_ptr(), solver.x.device_ptr_overwrite(), C.byref(opts), C.byref(info))
 
@@ -193,21 +209,32 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = world * n_dofs / (ms_per_step * 1e-3)
-    rel_res = info.residual_norm / info.rhs_norm
+    value = n_dofs_total / (ms_per_step * 1e-3)
     # true residual of the final iterate (one extra SpMV, outside the timed region)
-    opts_chk = solver.solve_options()
-    opts_chk.final_residual = 1
-    info_chk = _lib.SolveInfo()
-    dev.call("nxfx_solve", solver.b.device_ptr(), solver.x.device_ptr_overwrite(), C.byref(opts_chk), C.byref(info_chk))
-    rel_res_final = info_chk.residual_norm / info_chk.rhs_norm
+    if ds is not None:
+        hist = ds.solve(refine_steps=1, final_residual=True)
+        rel_res, rel_res_final = hist[0], hist[-1]
+    else:
+        rel_res = info.residual_norm / info.rhs_norm
+        opts_chk = solver.solve_options()
+        opts_chk.final_residual = 1
+        info_chk = _lib.SolveInfo()
+        dev.call("nxfx_solve", solver.b.device_ptr(), solver.x.device_ptr_overwrite(), C.byref(opts_chk), C.byref(info_chk))
+        rel_res_final = info_chk.residual_norm / info_chk.rhs_norm
 
     # ---- e2e through the Python API with host buffers --------------------------------------
     pbc_pinned = dev.pinned(nv)
     pbc_pinned[:] = asm._pbc_host
 
+    x_host = dev.pinned(n_dofs) if ds is not None else None
+
     def step_e2e():
         asm.compute_forms(p_bc_ex=pbc_pinned)  # H2D of the boundary data
+        if ds is not None:
+            ds.assemble()
+            ds.solve()
+            solver.x.d.download(x_host)  # D2H of the local part of the solution
+            return
         solver.assemble()
         solver.solve(functions)  # D2H of the solution blocks
 
@@ -223,7 +250,7 @@ def run_gpu(args):
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * n_dofs * args.steps / e2e_s
+    e2e_value = n_dofs_total * args.steps / e2e_s
     clocks = sampler.stop()
 
     # ---- per-kernel roofline (CUDA events on the launching stream) ---------------------------
@@ -252,15 +279,18 @@ def run_gpu(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": workload_name(n), "n_dofs_per_gpu": n_dofs, "nnz_per_gpu": nnz, "graph_edges": E,
+            "workload": workload_name(n), "n_dofs_total": n_dofs_total, "n_dofs_per_gpu": n_dofs, "nnz_per_gpu": nnz,
+            "graph_edges_per_gpu": E,
             "solver": "preonly: network-Schur direct solve + 1 iterative-refinement step (residual of the first solve checked)",
             "relative_residual_before_refinement": rel_res, "relative_residual_final": rel_res_final,
-            "partition": "one independent tree per GPU (zero-cut edge partition of an N-tree forest)" if world > 1 else "single GPU",
+            "partition": (f"one {n}-generation tree cut into {world} edge partitions (subtrees); {ds.part.n_top} cut multipliers "
+                          "replicated; per solve: 1 all-reduce (setup) + 2 (preconditioner) + 1 (shared rows of A x) + 1 (norms), "
+                          "torch.distributed/NCCL") if world > 1 else "single GPU",
             "l2": "per-step working set ~0.6 GB > 126 MB L2, no flush",
         },
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * nv), "d2h_bytes_per_step": int(8 * n_dofs),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * nv) * world, "d2h_bytes_per_step": int(8 * n_dofs) * world,
                 "path": "assembler.compute_forms(p_bc array) + solver.assemble() + solver.solve(functions)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -319,6 +349,9 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.generations
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and args.scaling == "weak":
+        n += max(0, (world - 1).bit_length())  # same workload rule as the GPU arm
     est = 8.0 * 4 ** (n - 20) if n >= 20 else 8.0 / 4 ** (20 - n)
     n_ref = n
     while n_ref > 10 and est * (args.steps + args.warmup) > 150.0:
@@ -354,6 +387,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--generations", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = n + log2(N) generations (one ~20-generation subtree per GPU), strong = same tree")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
