@@ -265,3 +265,48 @@ def test_full_size_properties():
     lu = net.lm_index[net.edges[:, 0]]
     pu = np.where(lu >= 0, lam[np.maximum(lu, 0)], -net.eval_pbc(P_Y)[net.edges[:, 0]])
     np.testing.assert_allclose(x[nq:nq + nc], pu - q_edge * h / 2, rtol=1e-8, atol=1e-11)
+
+
+def _graph(points, edges):
+    G = nx.DiGraph()
+    for i, p in enumerate(points):
+        G.add_node(i, pos=np.asarray(p, dtype=float))
+    for e in edges:
+        G.add_edge(*e)
+    return G
+
+
+def test_edge_cases_no_bifurcation_star_and_long_chain():
+    """Degenerate inputs: a single edge (no multipliers at all), a degree-6 star, a 30-node line
+    (tests/test_orientation.py graph) and a 200-node chain whose elimination tree has more levels
+    than the shared-memory sweep kernels hold (global-memory fallback sweeps)."""
+    cases = [
+        (_graph([(0, 0, 0), (1, 2, 0.5)], [(0, 1)]), 5),
+        (_graph([(0, 0, 0), (0, 1, 0)] + [(np.cos(k), 2 + np.sin(k), 0.1 * k) for k in range(5)],
+                [(0, 1)] + [(1, 2 + k) for k in range(5)]), 3),
+        (helpers.linear_graph(30, dim=3, ordered=lambda k: k % 3 != 0), 2),
+        (helpers.linear_graph(200, dim=2), 1),
+    ]
+    for G, N in cases:
+        for strategy in (None, "largest_first"):
+            nm, asm, solver, sol, net, A, b = run_case(G, N, strategy, lambda x: 1.0 + x[0] + 2 * x[1])
+            check_system(solver, net, A, b)
+            check_solution(sol, net, A, b)
+    assert not solver.assembler.network.device is None
+
+
+def test_update_positions_and_reassemble():
+    """Same topology, new coordinates / boundary data: re-assembly overwrites and the solve follows."""
+    G = ng.make_tree(6, 2, 3)
+    nm, asm, solver, sol, net, A, b = run_case(G, 2, "smallest_last", P_Y)
+    x1 = np.concatenate([f.x.array for f in sol]).copy()
+    asm.compute_forms(p_bc_ex=lambda x: 3.0 * x[1], R=2.0)
+    solver.assemble()
+    sol2 = solver.solve()
+    A2, b2 = net.assemble(net.eval_pbc(lambda x: 3.0 * x[1]), R=2.0)
+    check_system(solver, net, A2, b2)
+    x2 = np.concatenate([f.x.array for f in sol2])
+    assert helpers.rel_l2(x2, net.solve(A2, b2)) < 1e-10
+    nq = net.poff
+    assert helpers.rel_l2(x2[:nq], 1.5 * x1[:nq]) < 1e-10  # q ~ p_bc / R
+    assert helpers.rel_l2(x2[nq:], 3.0 * x1[nq:]) < 1e-10  # p, lambda ~ p_bc
