@@ -79,9 +79,17 @@ struct VertexRec {
 };
 
 // one 32-byte sector per vertex: coordinates and the boundary pressure travel together
+// (sm_100a: one 256-bit load per record with NXFX_V256, which also allows the L2 evict_last hint)
 __device__ __forceinline__ VertexRec load_vertex(const double2* __restrict__ x2, int v) {
-  const double2 a = __ldg(x2 + 2 * (size_t)v), b = __ldg(x2 + 2 * (size_t)v + 1);
+  const double2* p = x2 + 2 * (size_t)v;
+#ifdef NXFX_V256
+  double ax, ay, bx, by;
+  asm volatile("ld.global.L2::evict_last.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(ax), "=d"(ay), "=d"(bx), "=d"(by) : "l"(p));
+  return VertexRec{ax, ay, bx, by};
+#else
+  const double2 a = __ldg(p), b = __ldg(p + 1);
   return VertexRec{a.x, a.y, b.x, b.y};
+#endif
 }
 
 __device__ __forceinline__ double seg_length(const VertexRec& v0, const VertexRec& v1) {
@@ -336,6 +344,18 @@ constexpr int kAsmCap = 2560;  // 512 rows * 5 entries (N == 1)  >=  256 rows * 
 constexpr int kPresRows = 512;
 constexpr int kLamRows = 256;
 
+// The value / rhs streams are written once and not re-read by this kernel: streaming (evict-first)
+// stores keep them from pushing the vertex records out of L2.
+#ifndef NXFX_ASM_NOHINT
+#define NXFX_ST2(ptr, v) __stcs((ptr), (v))
+#define NXFX_ST1(ptr, v) __stcs((ptr), (v))
+#define NXFX_LDS(ptr) __ldcs(ptr)
+#else
+#define NXFX_ST2(ptr, v) (*(ptr) = (v))
+#define NXFX_ST1(ptr, v) (*(ptr) = (v))
+#define NXFX_LDS(ptr) (*(ptr))
+#endif
+
 template <bool ACC>
 __device__ __forceinline__ void store_pair(double* __restrict__ vals, size_t idx, double v0, double v1) {
   // idx even => 16-byte aligned (vals comes from cudaMalloc)
@@ -343,7 +363,7 @@ __device__ __forceinline__ void store_pair(double* __restrict__ vals, size_t idx
     double2* dst = reinterpret_cast<double2*>(vals + idx);
     double2 v = make_double2(v0, v1);
     if (ACC) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
-    *dst = v;
+    NXFX_ST2(dst, v);
   } else {
     if (ACC) { vals[idx] += v0; vals[idx + 1] += v1; } else { vals[idx] = v0; vals[idx + 1] = v1; }
   }
@@ -362,7 +382,7 @@ __device__ __forceinline__ void flush_tile(const double* sm, double* __restrict_
       double2 v = *reinterpret_cast<const double2*>(sm + i);
       double2* dst = reinterpret_cast<double2*>(out + i);
       if (ACC) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
-      *dst = v;
+      NXFX_ST2(dst, v);
     } else {
       if (i >= lo && i < hi) { if (ACC) out[i] += sm[i]; else out[i] = sm[i]; }
       if (i + 1 >= lo && i + 1 < hi) { if (ACC) out[i + 1] += sm[i + 1]; else out[i + 1] = sm[i + 1]; }
@@ -382,20 +402,20 @@ __device__ __forceinline__ void flux_tile_n1(const Net& g, const Coef& c, const 
   const int r = r0 + 2 * threadIdx.x;
   if (r < rend) {
     const int slot = r >> 1;
-    const int4 t = g.slot_uvl[slot];
-    const int e = g.slot_edge[slot];
-    const int start = rowptr[r] - sbase;
+    const int4 t = NXFX_LDS(g.slot_uvl + slot);
+    const int e = NXFX_LDS(g.slot_edge + slot);
+    const int start = NXFX_LDS(rowptr + r) - sbase;
     const VertexRec v0 = load_vertex(g.x2, t.x), v1 = load_vertex(g.x2, t.y);
     const double R = c.R_cell ? c.R_cell[e] : c.R_const;
     const double m = __dmul_rn(R, seg_length(v0, v1));
-    c.cell_rh[e] = m;
+    NXFX_ST1(c.cell_rh + e, m);
     if (rhs) {
       // assembly.py:258-260: -p_bc at out_marker vertices (boundary START), +p_bc at in_marker (END)
       const double b0 = t.z < 0 ? -v0.p : 0.0, b1 = t.w < 0 ? v1.p : 0.0;
       double2* dst = reinterpret_cast<double2*>(b + r);  // r even
       double2 v = make_double2(b0, b1);
       if (ACC) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
-      *dst = v;
+      NXFX_ST2(dst, v);
     }
     if (lhs) {
       const double m3 = __dmul_rn(m, kThird), m6 = __dmul_rn(m, kSixth);
@@ -477,7 +497,7 @@ __device__ __forceinline__ void pressure_tile(const Net& g, const Coef& c, const
                                     load_vertex(g.x2, vertex_id(g, ce, ct.x, ct.y, j + 1)));
         bv = __dmul_rn(c.f_cell ? c.f_cell[cell] : c.f_const, h);
       }
-      if (ACC) b[r] += bv; else b[r] = bv;
+      if (ACC) b[r] += bv; else NXFX_ST1(b + r, bv);
     }
   }
 }
@@ -500,7 +520,7 @@ __device__ __forceinline__ void lambda_tile(const Net& g, const int32_t* __restr
     }
   }
   if (rhs && !ACC)
-    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) b[g.loff + i] = 0.0;
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) NXFX_ST1(b + g.loff + i, 0.0);
 }
 
 template <bool ACC, bool N1>

@@ -164,6 +164,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// streaming variant: the matrix is read once per product, so its lines are marked evict-first in
+// L2 and do not push out the x vector the gathers keep re-using
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                                uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
   const uint32_t addr = smem_u32(bar);
@@ -206,6 +221,9 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+#ifndef NXFX_SPMV_NOHINT
+  const uint64_t stream_policy = l2_evict_first_policy();
+#endif
   auto issue = [&](int tile, int s) {
     const int r0 = tile * kTileRows;
     const int nr = min(kTileRows, n - r0);
@@ -214,11 +232,19 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
     const int cnt4 = ((se + 3) & ~3) - s4;
     const uint32_t rbytes = (uint32_t)(((nr + 1) * 4 + 15) & ~15);
     mbar_expect_tx(full + s, (uint32_t)cnt4 * 12u + rbytes);
+#ifndef NXFX_SPMV_NOHINT
+    if (cnt4 > 0) {
+      bulk_g2s_stream(st[s].vals, vals + s4, (uint32_t)cnt4 * 8u, full + s, stream_policy);
+      bulk_g2s_stream(st[s].cols, colidx + s4, (uint32_t)cnt4 * 4u, full + s, stream_policy);
+    }
+    bulk_g2s_stream(st[s].rows, rowptr + r0, rbytes, full + s, stream_policy);
+#else
     if (cnt4 > 0) {
       bulk_g2s(st[s].vals, vals + s4, (uint32_t)cnt4 * 8u, full + s);
       bulk_g2s(st[s].cols, colidx + s4, (uint32_t)cnt4 * 4u, full + s);
     }
     bulk_g2s(st[s].rows, rowptr + r0, rbytes, full + s);
+#endif
   };
   if (tid == 0) {
     for (int k = 0; k < kStages - 1; ++k) {
@@ -241,7 +267,7 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
     const int r0 = tile * kTileRows;
     const int nr = min(kTileRows, n - r0);
     double bi = 0.0;
-    if (MODE == 1 && tid < nr) bi = b[r0 + tid];
+    if (MODE == 1 && tid < nr) bi = __ldcs(b + r0 + tid);
     mbar_wait(full + s, (uint32_t)((it / kStages) & 1));
     SpmvStage& S = st[s];
     const int base = S.rows[0];
@@ -270,11 +296,16 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
       const int rs = S.rows[tid] - base + off, re = S.rows[tid + 1] - base + off;
       double acc = 0.0;
       for (int k = rs; k < re; ++k) acc = __dadd_rn(acc, S.vals[k]);
+#ifdef NXFX_Y_STCS
+#define NXFX_YST(p, v) __stcs((p), (v))
+#else
+#define NXFX_YST(p, v) (*(p) = (v))
+#endif
       if (MODE == 0) {
-        y[r0 + tid] = acc;
+        NXFX_YST(y + r0 + tid, acc);
       } else {
         const double r = __dsub_rn(bi, acc);
-        y[r0 + tid] = r;
+        NXFX_YST(y + r0 + tid, r);
         nrm += r * r;
         nrb += bi * bi;
       }
