@@ -254,8 +254,8 @@ def run_gpu(args):
     e2e_value = n_dofs_total * args.steps / e2e_s
     # nvidia-smi needs ~0.2 s to deliver its first sample, the timed regions above are a few ms:
     # keep the GPU under the same load (untimed steps) until a handful of samples exist
-    t_load = time.perf_counter()
-    while len(sampler.lines) < 6 and time.perf_counter() - t_load < 4.0 and sampler.proc is not None:
+    # (a fixed count derived from the all-reduced step time, so that all ranks stay in lock-step)
+    for _ in range(min(5000, int(0.6 / max(ms_per_step * 1e-3, 1e-5)))):
         step_resident()
     dev.sync()
     clocks = sampler.stop()

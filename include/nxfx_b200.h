@@ -182,6 +182,25 @@ int nxfx_assemble_solve_host(nxfx_ctx* ctx, const double* node_pos_h, const doub
                              double R_const, double f_const, const nxfx_solve_opts* opts,
                              double* x_h, nxfx_solve_info* info);
 
+/* ---- (7) table-driven assembly for higher-order elements ------------------------------------- *
+ * flux_degree / pressure_degree other than (1, 0): assembly.py:127-146 (spaces) + :253-277 (forms)
+ * with P_fd flux and continuous P_pd pressure.  The pattern and the contribution lists come from
+ * the host (networks_fenicsx_b200/generic.py):
+ *   rowptr_h [n_dofs+1], colidx_h [nnz]   CSR pattern (explicit zeros included)
+ *   src_id_h [nnz][2]   cell | (1<<30 if the value is coef * R*h of the cell), or -1
+ *   src_coef_h [nnz][2] reference-element coefficient (M_ref, +-B_ref, +-trace)
+ *   bsrc_ptr_h [n_dofs+1], bsrc_id_h, bsrc_coef_h   right-hand-side sources per row:
+ *                       cell -> coef * f*h, vertex | (1<<30) -> coef * p_bc(vertex)
+ * nxfx_assemble_generic has the semantics of nxfx_assemble.  nxfx_spmv / nxfx_solve (FGMRES with
+ * pc none|jacobi) work on the resulting matrix.                                                    */
+int nxfx_set_generic_system(nxfx_ctx* ctx, int32_t n_dofs, int32_t n_flux_rows, int32_t nnz,
+                            const int32_t* rowptr_h, const int32_t* colidx_h, const int32_t* src_id_h,
+                            const double* src_coef_h, const int32_t* bsrc_ptr_h,
+                            const int32_t* bsrc_id_h, const double* bsrc_coef_h);
+int nxfx_assemble_generic(nxfx_ctx* ctx, const double* R_cell_d, double R_const,
+                          const double* f_cell_d, double f_const, int lhs, int rhs, int accumulate,
+                          double* b_d);
+
 /* ---- (6) multi-GPU: one rank's part of a partitioned network ------------------------------------ *
  * Replaces what MPI does inside DOLFINx/PETSc/MUMPS at assembly.py:355-367 and solver.py:127-132
  * (stash exchange, ghost updates, distributed LU).  The ctx holds one rank's sub-network in which

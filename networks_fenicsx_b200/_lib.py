@@ -103,6 +103,14 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.POINTER(SolveOpts),
          C.c_void_p, C.POINTER(SolveInfo)],
     ),
+    "nxfx_set_generic_system": (
+        C.c_int,
+        [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_f64p, c_i32p, c_i32p, c_f64p],
+    ),
+    "nxfx_assemble_generic": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    ),
     "nxfx_set_shared": (C.c_int, [C.c_void_p, C.c_int32, c_i32p, c_f64p]),
     "nxfx_top_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "nxfx_pc_setup_begin": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -88,28 +88,40 @@ class HydraulicNetworkAssembler:
 
     @timed("nxfx:HydraulicNetworkAssembler:__init__")
     def __init__(self, mesh: NetworkMesh, flux_degree: int = 1, pressure_degree: int = 0):
-        if flux_degree != 1 or pressure_degree != 0:
-            raise NotImplementedError(
-                "the B200 path implements flux_degree=1 / pressure_degree=0 (the reference's "
-                "defaults, used by every demo); higher orders are listed under 'next' in DESIGN.md"
-            )
+        flux_degree, pressure_degree = int(flux_degree), int(pressure_degree)
+        if flux_degree < 1 or pressure_degree < 0 or flux_degree > 4 or pressure_degree > 3:
+            raise ValueError("flux_degree in 1..4 and pressure_degree in 0..3 are supported")
         self._network_mesh = mesh
+        self._degrees = (flux_degree, pressure_degree)
+        # (1, 0) -- the reference's defaults, used by every demo -- runs on the specialised kernels;
+        # other degrees use the table-driven path (generic.py / generic.cuh)
+        self._generic = None
+        if self._degrees != (1, 0):
+            from .generic import build_generic_system  # noqa: PLC0415
+
+            self._generic = build_generic_system(mesh, flux_degree, pressure_degree)
         N = mesh.cells_per_edge
         E = mesh.graph_edges.shape[0]
         C_ = mesh.num_edge_colors
         counts = mesh._color_count
-        qoff = np.concatenate([[0], np.cumsum(counts * (N + 1))])
+        per_edge = flux_degree * N + 1
+        qoff = np.concatenate([[0], np.cumsum(counts * per_edge)])
         self._flux_spaces = _FluxSpaces(mesh, qoff, flux_degree)
+        nv = mesh.mesh.topology.index_map(0).size_local
+        n_p = N * E if pressure_degree == 0 else nv + (pressure_degree - 1) * N * E
+        if pressure_degree == 0:
+            pdofs = lambda: np.arange(N * E, dtype=np.int32)[:, None]  # noqa: E731
+        else:
+            pdofs = lambda: (self._generic.cell_pressure_dofs - int(qoff[-1])).astype(np.int32)  # noqa: E731
         self._pressure_space = FunctionSpace(
-            mesh.mesh, pressure_degree, True, N * E, int(qoff[-1]),
-            lambda: np.arange(N * E, dtype=np.int32)[:, None], "pressure",
+            mesh.mesh, pressure_degree, pressure_degree == 0, n_p, int(qoff[-1]), pdofs, "pressure",
         )
         n_bif = mesh.bifurcation_values.size
         self._lm_space = FunctionSpace(
-            mesh.lm_mesh, 0, True, n_bif, int(qoff[-1]) + N * E,
+            mesh.lm_mesh, 0, True, n_bif, int(qoff[-1]) + n_p,
             lambda: np.arange(n_bif, dtype=np.int32)[:, None], "lm",
         )
-        self._block_sizes = [int(c) * (N + 1) for c in counts] + [N * E, n_bif]
+        self._block_sizes = [int(c) * per_edge for c in counts] + [n_p, n_bif]
         self._n_dofs = int(sum(self._block_sizes))
         # integration data (assembly.py:152-162)
         self._integration_data = []
@@ -223,6 +235,16 @@ class HydraulicNetworkAssembler:
         return self._block_sizes
 
     @property
+    def degrees(self) -> tuple[int, int]:
+        """(flux_degree, pressure_degree)"""
+        return self._degrees
+
+    @property
+    def is_generic(self) -> bool:
+        """True when the table-driven higher-order path is used."""
+        return self._generic is not None
+
+    @property
     def num_dofs(self) -> int:
         return self._n_dofs
 
@@ -260,7 +282,19 @@ class HydraulicNetworkAssembler:
             raise RuntimeError("compute_forms() must be called before creating the matrix")
         dev = self._network_mesh.device
         if not self._symbolic_done:
-            dev.call("nxfx_symbolic")
+            if self._generic is None:
+                dev.call("nxfx_symbolic")
+            else:
+                from . import _lib  # noqa: PLC0415
+
+                g = self._generic
+                c32 = lambda a: _lib.as_i32p(np.ascontiguousarray(a, dtype=np.int32))  # noqa: E731
+                c64 = lambda a: _lib.as_f64p(np.ascontiguousarray(a, dtype=np.float64))  # noqa: E731
+                dev.call(
+                    "nxfx_set_generic_system", g.n_dofs, g.n_flux, g.colidx.size, c32(g.rowptr), c32(g.colidx),
+                    c32(g.src_id), c64(g.src_coef), c32(g.bsrc_ptr), c32(g.bsrc_id), c64(g.bsrc_coef),
+                )
+                dev.sync()
             self._symbolic_done = True
         nnz = C.c_int64()
         dev.call("nxfx_get_sizes", None, None, None, C.byref(nnz))
@@ -308,7 +342,7 @@ class HydraulicNetworkAssembler:
         R_d, R_c = self._R
         f_d, f_c = self._f
         dev.call(
-            "nxfx_assemble",
+            "nxfx_assemble" if self._generic is None else "nxfx_assemble_generic",
             R_d.c_ptr if R_d is not None else None, C.c_double(R_c),
             f_d.c_ptr if f_d is not None else None, C.c_double(f_c),
             int(bool(assemble_lhs)), int(bool(assemble_rhs)), int(acc), b_ptr,
@@ -340,13 +374,17 @@ class _FluxSpaces:
         if c not in self._cache:
             N = self._mesh.cells_per_edge
             n_edges = int(self._mesh._color_count[c])
+            fd = self._degree
+            per_edge = fd * N + 1
 
-            def cell_dofs(n_edges=n_edges, N=N):
-                base = (np.arange(n_edges)[:, None] * (N + 1) + np.arange(N)[None, :]).ravel()
-                return np.stack([base, base + 1], axis=1)
+            def cell_dofs(n_edges=n_edges, N=N, fd=fd, per_edge=per_edge):
+                eb = np.repeat(np.arange(n_edges) * per_edge, N)
+                j = np.tile(np.arange(N), n_edges)
+                cols = [eb + j, eb + j + 1] + [eb + (N + 1) + j * (fd - 1) + i for i in range(fd - 1)]
+                return np.stack(cols, axis=1)
 
             self._cache[c] = FunctionSpace(
-                self._mesh.submeshes[c], self._degree, False, n_edges * (N + 1), int(self._qoff[c]),
+                self._mesh.submeshes[c], fd, False, n_edges * per_edge, int(self._qoff[c]),
                 cell_dofs, f"flux_{c}",
             )
         return self._cache[c]

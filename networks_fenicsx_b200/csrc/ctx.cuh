@@ -71,6 +71,10 @@ struct nxfx_ctx {
   // pattern + values
   nxfx::DevBuf<int32_t> rowptr, colidx, tile_base;
   bool pipe_ok = false;  // every row tile fits one pipeline stage
+  // table-driven (higher-order) assembly
+  bool generic = false;
+  nxfx::DevBuf<int32_t> gen_src_id, gen_bptr, gen_bid;
+  nxfx::DevBuf<double> gen_src_coef, gen_bcoef, gen_cell_h;
   nxfx::DevBuf<double> vals;
   nxfx::DevBuf<double> cell_rh;  // [nc] R*h per cell, written by the assembly kernel
   // solver workspace

@@ -8,6 +8,7 @@
 
 #include "assemble.cuh"
 #include "ctx.cuh"
+#include "generic.cuh"
 #include "precond.cuh"
 #include "spmv.cuh"
 
@@ -412,6 +413,26 @@ int solve_fgmres(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opt
   return NXFX_OK;
 }
 
+// row tiles of the pipelined SpMV (shared by the symbolic phase and the generic pattern upload)
+int setup_spmv_tiles(nxfx_ctx* ctx) {
+  const int n = (int)ctx->ndofs;
+  const int ntiles = (int)cdiv(n, kTileRows);
+  NXFX_CUDA(ctx, ctx->tile_base.alloc((size_t)ntiles + 2));
+  int32_t* max_tile = reinterpret_cast<int32_t*>(ctx->ticket.p);  // borrowed, reset below
+  NXFX_LAUNCH(ctx, tile_base_kernel, (int)cdiv(ntiles + 1, kThreads), kThreads, 0, n, ntiles, ctx->rowptr.p,
+              ctx->tile_base.p, max_tile);
+  int32_t max_tile_h = 0;
+  NXFX_CUDA(ctx, cudaMemcpyAsync(&max_tile_h, max_tile, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned int), ctx->stream));
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->pipe_ok = max_tile_h + 8 <= kPipeCap;
+  if (ctx->pipe_ok) {
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(spmv_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(spmv_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+  }
+  return NXFX_OK;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -608,6 +629,8 @@ int nxfx_mesh_geometry_device(nxfx_ctx* ctx, const double** x) {
 int nxfx_symbolic(nxfx_ctx* ctx) {
   if (!ctx) return NXFX_ERR_INVALID;
   NXFX_REQUIRE(ctx, ctx->has_network, "no network");
+  int rc;
+  ctx->generic = false;
   const int n = (int)ctx->ndofs;
   Net g = make_net(ctx);
   DevBuf<int32_t> len;
@@ -631,21 +654,7 @@ int nxfx_symbolic(nxfx_ctx* ctx) {
   NXFX_CUDA(ctx, cudaMemsetAsync(ctx->colidx.p, 0, ((size_t)nnz + 8) * sizeof(int32_t), ctx->stream));
   NXFX_CUDA(ctx, cudaMemsetAsync(ctx->vals.p, 0, ((size_t)nnz + 8) * sizeof(double), ctx->stream));
   NXFX_LAUNCH(ctx, fill_cols_kernel, (int)cdiv(n, kThreads), kThreads, 0, g, ctx->rowptr.p, ctx->colidx.p);
-  // row tiles of the pipelined SpMV
-  const int ntiles = (int)cdiv(n, kTileRows);
-  NXFX_CUDA(ctx, ctx->tile_base.alloc((size_t)ntiles + 2));
-  int32_t* max_tile = reinterpret_cast<int32_t*>(ctx->ticket.p);  // borrowed, reset below
-  NXFX_LAUNCH(ctx, tile_base_kernel, (int)cdiv(ntiles + 1, kThreads), kThreads, 0, n, ntiles, ctx->rowptr.p,
-              ctx->tile_base.p, max_tile);
-  int32_t max_tile_h = 0;
-  NXFX_CUDA(ctx, cudaMemcpyAsync(&max_tile_h, max_tile, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned int), ctx->stream));
-  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->pipe_ok = max_tile_h + 8 <= kPipeCap;
-  if (ctx->pipe_ok) {
-    NXFX_CUDA(ctx, cudaFuncSetAttribute(spmv_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
-    NXFX_CUDA(ctx, cudaFuncSetAttribute(spmv_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
-  }
+  if ((rc = setup_spmv_tiles(ctx))) return rc;
   ctx->has_pattern = true;
   ctx->assembled = false;
   return NXFX_OK;
@@ -673,6 +682,7 @@ int nxfx_assemble(nxfx_ctx* ctx, const double* R_cell, double R_const, const dou
                   double f_const, int lhs, int rhs, int accumulate, double* b) {
   if (!ctx) return NXFX_ERR_INVALID;
   NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
+  NXFX_REQUIRE(ctx, !ctx->generic, "higher-order pattern loaded: use nxfx_assemble_generic");
   NXFX_REQUIRE(ctx, !rhs || (b && ctx->has_pbc), "rhs requested without b / boundary pressure");
   if (!lhs && !rhs) return NXFX_OK;
   Net g = make_net(ctx);
@@ -814,6 +824,8 @@ int nxfx_solve(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts*
   NXFX_REQUIRE(ctx, ctx->assembled, "matrix has not been assembled");
   std::memset(info, 0, sizeof *info);
   int rc;
+  if (opts->pc_type == NXFX_PC_NETWORK_SCHUR && ctx->generic)
+    return fail(ctx, NXFX_ERR_UNSUPPORTED, "the network Schur preconditioner is implemented for flux P1 / pressure DG0");
   if (opts->pc_type == NXFX_PC_NETWORK_SCHUR && !ctx->pc_ready)
     if ((rc = do_pc_setup(ctx))) return rc;
   if (opts->ksp_type == NXFX_KSP_PREONLY) rc = solve_preonly(ctx, b, x, opts, info);
@@ -846,6 +858,85 @@ int nxfx_assemble_solve_host(nxfx_ctx* ctx, const double* node_pos, const double
   if ((rc = nxfx_solve(ctx, ctx->e2e_b.p, ctx->e2e_x.p, opts, info))) return rc;
   NXFX_CUDA(ctx, cudaMemcpyAsync(x_h, ctx->e2e_x.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NXFX_OK;
+}
+
+// ---- (7) table-driven assembly for higher-order elements ------------------------------------------
+int nxfx_set_generic_system(nxfx_ctx* ctx, int32_t n_dofs, int32_t n_flux_rows, int32_t nnz,
+                            const int32_t* rowptr, const int32_t* colidx, const int32_t* src_id,
+                            const double* src_coef, const int32_t* bsrc_ptr, const int32_t* bsrc_id,
+                            const double* bsrc_coef) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_network, "no network");
+  NXFX_REQUIRE(ctx, n_dofs > 0 && nnz > 0 && n_flux_rows >= 0 && n_flux_rows <= n_dofs, "bad sizes");
+  NXFX_REQUIRE(ctx, rowptr && colidx && src_id && src_coef && bsrc_ptr, "null input");
+  NXFX_REQUIRE(ctx, rowptr[0] == 0 && rowptr[n_dofs] == nnz, "rowptr does not match nnz");
+  const int64_t nc = ctx->nc;
+  for (int64_t k = 0; k < 2 * (int64_t)nnz; ++k) {
+    const int32_t s = src_id[k];
+    if (s >= 0 && (s & (kRhFlag - 1)) >= nc) return fail(ctx, NXFX_ERR_INVALID, "src_id[%lld] out of range", (long long)k);
+  }
+  for (int32_t k = 0; k < nnz; ++k)
+    if (colidx[k] < 0 || colidx[k] >= n_dofs) return fail(ctx, NXFX_ERR_INVALID, "colidx[%d] out of range", k);
+  const int32_t nb = bsrc_ptr[n_dofs];
+  for (int32_t k = 0; k < nb; ++k) {
+    const int32_t i = bsrc_id[k];
+    const int64_t lim = (i & kVertexFlag) ? ctx->nv : nc;
+    if (i < 0 || (i & (kVertexFlag - 1)) >= lim) return fail(ctx, NXFX_ERR_INVALID, "bsrc_id[%d] out of range", k);
+  }
+  int rc;
+  ctx->has_pattern = ctx->assembled = ctx->pc_ready = false;
+  ctx->ndofs = n_dofs; ctx->nq = n_flux_rows; ctx->nnz = nnz;
+  ctx->poff = n_flux_rows; ctx->loff = n_dofs - ctx->n_bif;
+  NXFX_CUDA(ctx, ctx->rowptr.alloc((size_t)n_dofs + 9));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->rowptr.p, 0, ((size_t)n_dofs + 9) * sizeof(int32_t), ctx->stream));
+  NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->rowptr.p, rowptr, ((size_t)n_dofs + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  NXFX_CUDA(ctx, ctx->colidx.alloc((size_t)nnz + 8));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->colidx.p, 0, ((size_t)nnz + 8) * sizeof(int32_t), ctx->stream));
+  NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->colidx.p, colidx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  NXFX_CUDA(ctx, ctx->vals.alloc((size_t)nnz + 8));
+  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->vals.p, 0, ((size_t)nnz + 8) * sizeof(double), ctx->stream));
+  if ((rc = upload(ctx, ctx->gen_src_id, src_id, (size_t)2 * nnz))) return rc;
+  if ((rc = upload(ctx, ctx->gen_src_coef, src_coef, (size_t)2 * nnz))) return rc;
+  if ((rc = upload(ctx, ctx->gen_bptr, bsrc_ptr, (size_t)n_dofs + 1))) return rc;
+  if ((rc = upload(ctx, ctx->gen_bid, bsrc_id, (size_t)nb))) return rc;
+  if ((rc = upload(ctx, ctx->gen_bcoef, bsrc_coef, (size_t)nb))) return rc;
+  NXFX_CUDA(ctx, ctx->gen_cell_h.alloc((size_t)nc));
+  if ((rc = setup_spmv_tiles(ctx))) return rc;
+  ctx->generic = true;
+  ctx->has_pattern = true;
+  return NXFX_OK;
+}
+
+int nxfx_assemble_generic(nxfx_ctx* ctx, const double* R_cell, double R_const, const double* f_cell,
+                          double f_const, int lhs, int rhs, int accumulate, double* b) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_pattern && ctx->generic, "nxfx_set_generic_system has not been called");
+  NXFX_REQUIRE(ctx, !rhs || (b && ctx->has_pbc), "rhs requested without b / boundary pressure");
+  if (!lhs && !rhs) return NXFX_OK;
+  Net g = make_net(ctx);
+  NXFX_LAUNCH(ctx, cell_length_kernel, vec_grid(ctx, ctx->nc), kThreads, 0, g, ctx->gen_cell_h.p);
+  if (lhs) {
+    const int2* sid = reinterpret_cast<const int2*>(ctx->gen_src_id.p);
+    const double2* sco = reinterpret_cast<const double2*>(ctx->gen_src_coef.p);
+    if (accumulate)
+      NXFX_LAUNCH(ctx, assemble_generic_kernel<true>, vec_grid(ctx, ctx->nnz), kThreads, 0, ctx->nnz, sid, sco,
+                  ctx->gen_cell_h.p, R_cell, R_const, ctx->vals.p);
+    else
+      NXFX_LAUNCH(ctx, assemble_generic_kernel<false>, vec_grid(ctx, ctx->nnz), kThreads, 0, ctx->nnz, sid, sco,
+                  ctx->gen_cell_h.p, R_cell, R_const, ctx->vals.p);
+    ctx->assembled = true;
+    ctx->pc_ready = false;
+  }
+  if (rhs) {
+    const int n = (int)ctx->ndofs;
+    if (accumulate)
+      NXFX_LAUNCH(ctx, rhs_generic_kernel<true>, (int)cdiv(n, kThreads), kThreads, 0, n, ctx->gen_bptr.p, ctx->gen_bid.p,
+                  ctx->gen_bcoef.p, ctx->gen_cell_h.p, f_cell, f_const, g.x2, b);
+    else
+      NXFX_LAUNCH(ctx, rhs_generic_kernel<false>, (int)cdiv(n, kThreads), kThreads, 0, n, ctx->gen_bptr.p, ctx->gen_bid.p,
+                  ctx->gen_bcoef.p, ctx->gen_cell_h.p, f_cell, f_const, g.x2, b);
+  }
   return NXFX_OK;
 }
 

@@ -30,6 +30,16 @@ def extract_global_flux(graph_mesh: NetworkMesh, functions: list[Function]) -> F
         lambda: np.arange((q_degree + 1) * nc, dtype=np.int32).reshape(nc, q_degree + 1), "global_flux",
     )
     dev = graph_mesh.device
+    if q_degree != 1:
+        # higher order: host gather through the cell -> dof tables of the per-colour spaces
+        global_q = Function(V, name="Global_Flux")
+        out = global_q.x.array.reshape(nc, q_degree + 1)
+        for i, flux in enumerate(flux_functions):
+            flux.name = f"Flux_{i}"
+            cells = graph_mesh.entity_maps[i].sub_topology_to_topology(
+                np.arange(flux.function_space.dofmap.list.shape[0], dtype=np.int32))
+            out[cells] = flux.x.array[flux.function_space.dofmap.list]
+        return global_q
     global_q = Function(V, name="Global_Flux", array=dev.pinned(V.num_dofs))
     nq = sum(f.x.array.size for f in flux_functions)
     xq = dev.empty(nq)

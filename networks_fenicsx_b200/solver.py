@@ -117,6 +117,17 @@ class Solver:
         ksp_type = str(o.get("ksp_type", "preonly")).lower()
         pc_type = str(o.get("pc_type", "lu")).lower()
         opts = _lib.SolveOpts()
+        if self.assembler.is_generic and pc_type in _DIRECT_PCS:
+            # higher-order elements: the network Schur condensation is implemented for P1/DG0;
+            # direct-solver accuracy is obtained with (long-restart) GMRES instead
+            opts.pc_type = _lib.PC_JACOBI_FLUX
+            opts.ksp_type = _lib.KSP_FGMRES
+            opts.rtol = float(o.get("ksp_rtol", 1e-12))
+            opts.atol = float(o.get("ksp_atol", 1e-50))
+            opts.max_it = int(o.get("ksp_max_it", 20000))
+            opts.restart = int(o.get("ksp_gmres_restart", min(self.assembler.num_dofs, 200)))
+            opts.error_if_not_converged = int(bool(o.get("ksp_error_if_not_converged", False)))
+            return opts
         if pc_type in _DIRECT_PCS:
             opts.pc_type = _lib.PC_NETWORK_SCHUR
         elif pc_type == "none":

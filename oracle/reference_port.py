@@ -424,3 +424,130 @@ class OracleNetwork:
         pu = np.where(lu >= 0, lam[np.maximum(lu, 0)] if nb else 0.0, -pbc_vertex[u])
         pv = np.where(lv >= 0, lam[np.maximum(lv, 0)] if nb else 0.0, -pbc_vertex[v])
         return g * (pu - pv), lam
+
+
+# --------------------------------------------------------------------------------------
+# Higher-order elements: flux P_fd (continuous per edge), pressure DG0 (pd = 0) or continuous
+# P_pd on the parent mesh (pd >= 1) -- assembly.py:127-146.  Equispaced Lagrange, dof order on a
+# cell [X=0, X=1, interior ascending] (basix "equispaced" variant; interval cells need no
+# permutations).  Literal COO assembly; canonical numbering: flux dofs of an
+# edge = [N+1 vertex dofs, then fd-1 interior dofs per cell], pressure dofs = [mesh vertices, then
+# pd-1 interior dofs per cell].
+# --------------------------------------------------------------------------------------
+def lagrange_nodes(d):
+    if d == 0:
+        return np.array([0.5])
+    return np.concatenate([[0.0, 1.0], np.arange(1, d) / d])
+
+
+def lagrange_tables(fd, pd):
+    """(M_ref[fd+1,fd+1], B_ref[pd+1,fd+1], w_ref[pd+1], trace0[fd+1], trace1[fd+1]) by exact
+    Gauss-Legendre quadrature: M = int phi_a phi_b, B = int psi_r phi_a', w = int psi_r
+    (SURVEY A.3)."""
+    from numpy.polynomial import polynomial as P
+
+    def basis(d):
+        x = lagrange_nodes(d)
+        if d == 0:
+            return [np.array([1.0])]
+        out = []
+        for i in range(d + 1):
+            c = np.array([1.0])
+            for j in range(d + 1):
+                if j != i:
+                    c = P.polymul(c, np.array([-x[j], 1.0]) / (x[i] - x[j]))
+            out.append(c)
+        return out
+
+    phi, psi = basis(fd), basis(pd)
+    gx, gw = np.polynomial.legendre.leggauss(fd + pd + 2)
+    X, W = 0.5 * (gx + 1.0), 0.5 * gw
+    ph = np.array([P.polyval(X, c) for c in phi])
+    dph = np.array([P.polyval(X, P.polyder(c)) if c.size > 1 else 0 * X for c in phi])
+    ps = np.array([P.polyval(X, c) for c in psi])
+    M = (ph * W) @ ph.T
+    B = (ps * W) @ dph.T
+    w = ps @ W
+    t0 = np.array([P.polyval(0.0, c) for c in phi])
+    t1 = np.array([P.polyval(1.0, c) for c in phi])
+    return M, B, w, np.round(t0), np.round(t1)
+
+
+class OracleNetworkHO(OracleNetwork):
+    """Higher-order oracle (small / medium cases; loop-free COO but not tuned)."""
+
+    def __init__(self, pos, edges, colors, N, flux_degree, pressure_degree):
+        super().__init__(pos, edges, colors, N)
+        fd, pd = int(flux_degree), int(pressure_degree)
+        self.fd, self.pd = fd, pd
+        E, N = self.E, self.N
+        count = np.bincount(self.colors, minlength=self.C)
+        per_edge = fd * N + 1
+        self.qoff = np.concatenate([[0], np.cumsum(count * per_edge)])
+        self.fb = self.qoff[self.colors] + self.rank * per_edge
+        self.poff = int(self.qoff[-1])
+        nv = self.x.shape[0]
+        self.n_p = N * E if pd == 0 else nv + (pd - 1) * N * E
+        self.loff = self.poff + self.n_p
+        self.n_dofs = self.loff + self.n_bif
+        self.block_sizes = [int(c) * per_edge for c in count] + [self.n_p, self.n_bif]
+        self.tables = lagrange_tables(fd, pd)
+
+    def cell_flux_dofs(self):
+        """[n_cells, fd+1] global flux dofs: [vertex j, vertex j+1, interior...]."""
+        E, N, fd = self.E, self.N, self.fd
+        e = np.repeat(np.arange(E), N)
+        j = np.tile(np.arange(N), E)
+        cols = [self.fb[e] + j, self.fb[e] + j + 1]
+        for i in range(fd - 1):
+            cols.append(self.fb[e] + (N + 1) + j * (fd - 1) + i)
+        return np.stack(cols, axis=1)
+
+    def cell_pressure_dofs(self):
+        E, N, pd = self.E, self.N, self.pd
+        nc = E * N
+        if pd == 0:
+            return self.poff + np.arange(nc)[:, None]
+        nv = self.x.shape[0]
+        cols = [self.poff + self.cells[:, 0], self.poff + self.cells[:, 1]]
+        for i in range(pd - 1):
+            cols.append(self.poff + nv + np.arange(nc) * (pd - 1) + i)
+        return np.stack(cols, axis=1)
+
+    def assemble(self, pbc_vertex, R=1.0, f=0.0):
+        M, B, w, t0, t1 = self.tables
+        E, N, fd, pd = self.E, self.N, self.fd, self.pd
+        h = self.cell_lengths()
+        nc = h.size
+        Rc = np.broadcast_to(np.asarray(R, dtype=np.float64), h.shape)
+        fc = np.broadcast_to(np.asarray(f, dtype=np.float64), h.shape)
+        m = Rc * h
+        qd, pdofs = self.cell_flux_dofs(), self.cell_pressure_dofs()
+        rows, cols, vals = [], [], []
+        for a in range(fd + 1):
+            for b_ in range(fd + 1):
+                rows.append(qd[:, a]); cols.append(qd[:, b_]); vals.append(m * M[a, b_])
+        for r in range(pd + 1):
+            for a in range(fd + 1):
+                rows.append(pdofs[:, r]); cols.append(qd[:, a]); vals.append(np.full(nc, B[r, a]))
+                rows.append(qd[:, a]); cols.append(pdofs[:, r]); vals.append(np.full(nc, -B[r, a]))
+        u, v = self.edges[:, 0], self.edges[:, 1]
+        ein = np.flatnonzero(self.lm_index[v] >= 0)
+        eout = np.flatnonzero(self.lm_index[u] >= 0)
+        last, first = ein * N + N - 1, eout * N
+        for a in range(fd + 1):  # full cell rows incl. explicit zeros (SURVEY A.3)
+            lin = self.loff + self.lm_index[v[ein]]
+            rows += [lin, qd[last, a]]; cols += [qd[last, a], lin]; vals += [np.full(ein.size, t1[a])] * 2
+            lout = self.loff + self.lm_index[u[eout]]
+            rows += [lout, qd[first, a]]; cols += [qd[first, a], lout]; vals += [np.full(eout.size, -t0[a])] * 2
+        A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                          shape=(self.n_dofs, self.n_dofs)).tocsr()
+        A.sort_indices()
+        b = np.zeros(self.n_dofs)
+        for r in range(pd + 1):
+            np.add.at(b, pdofs[:, r], fc * h * w[r])
+        outlet = np.flatnonzero(self.lm_index[v] < 0)
+        inlet = np.flatnonzero(self.lm_index[u] < 0)
+        np.add.at(b, self.fb[outlet] + N, pbc_vertex[v[outlet]])
+        np.add.at(b, self.fb[inlet], -pbc_vertex[u[inlet]])
+        return A, b
