@@ -229,11 +229,17 @@ int tree_pass(nxfx_ctx* ctx, bool factor) {
 int do_pc_setup(nxfx_ctx* ctx) {
   NXFX_REQUIRE(ctx, ctx->assembled, "assemble the matrix before pc_setup");
   NXFX_REQUIRE(ctx, ctx->tree.set, "nxfx_set_tree_schedule has not been called");
-  NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N,
-              ctx->cell_rh.p, ctx->edge_g.p);
+  const bool n1 = ctx->N == 1 && ctx->tree.fast_ok;  // (the global-memory fallback sweeps read edge_g)
+  if (!n1)
+    NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N,
+                ctx->cell_rh.p, ctx->edge_g.p);
   if (ctx->n_bif > 0) {
-    NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx),
-                make_tree(ctx), ctx->edge_g.p);
+    if (n1)
+      NXFX_LAUNCH(ctx, bif_diag_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx),
+                  make_tree(ctx), ctx->cell_rh.p);
+    else
+      NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx),
+                  make_tree(ctx), ctx->edge_g.p);
     int rc = tree_pass(ctx, true);
     if (rc) return rc;
   }
@@ -263,6 +269,18 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
   NXFX_REQUIRE(ctx, ctx->pc_ready, "pc_setup has not been run");
   Net g = make_net(ctx);
   TreeDev t = make_tree(ctx);
+  const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
+  if (ctx->N == 1 && ctx->tree.fast_ok) {
+    if (ctx->n_bif > 0) {
+      NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cell_rh.p,
+                  ctx->lam_weight.p);
+      int rc = tree_pass(ctx, false);
+      if (rc) return rc;
+    }
+    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+    return NXFX_OK;
+  }
   NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p,
               r, ctx->edge_c.p, ctx->edge_fn.p);
   if (ctx->n_bif > 0) {
@@ -271,7 +289,6 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
     int rc = tree_pass(ctx, false);
     if (rc) return rc;
   }
-  const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
   if (add)
     NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
   else
@@ -978,8 +995,12 @@ int nxfx_pc_setup_begin(nxfx_ctx* ctx, double* buf) {
   auto& s = ctx->tree;
   TreeDev t = make_tree(ctx);
   const int nb = s.n_chunks - 1;
-  NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N, ctx->cell_rh.p, ctx->edge_g.p);
-  NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx), t, ctx->edge_g.p);
+  if (ctx->N == 1) {
+    NXFX_LAUNCH(ctx, bif_diag_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx), t, ctx->cell_rh.p);
+  } else {
+    NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N, ctx->cell_rh.p, ctx->edge_g.p);
+    NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx), t, ctx->edge_g.p);
+  }
   if (nb > 0) NXFX_LAUNCH(ctx, tree_factor_kernel, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
   NXFX_LAUNCH(ctx, (tree_top_kernel<true, kPartial>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
   return NXFX_OK;
@@ -1002,9 +1023,13 @@ int nxfx_pc_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
   Net g = make_net(ctx);
   TreeDev t = make_tree(ctx);
   const int nb = ctx->tree.n_chunks - 1;
-  NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p, r, ctx->edge_c.p, ctx->edge_fn.p);
-  NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->edge_g.p, ctx->edge_c.p,
-              ctx->edge_fn.p, ctx->lam_weight.p);
+  if (ctx->N == 1) {
+    NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cell_rh.p, ctx->lam_weight.p);
+  } else {
+    NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p, r, ctx->edge_c.p, ctx->edge_fn.p);
+    NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->edge_g.p, ctx->edge_c.p,
+                ctx->edge_fn.p, ctx->lam_weight.p);
+  }
   if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
   NXFX_LAUNCH(ctx, (tree_top_kernel<false, kPartial>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
   return NXFX_OK;
@@ -1020,6 +1045,11 @@ int nxfx_pc_apply_end(nxfx_ctx* ctx, const double* r, double* z, double* buf, in
   NXFX_LAUNCH(ctx, (tree_top_kernel<false, kFinish>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
   if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
   const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
+  if (ctx->N == 1) {
+    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+    return NXFX_OK;
+  }
   if (add)
     NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
   else

@@ -511,6 +511,70 @@ edge_backsub_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh,
   }
 }
 
+// ---- N == 1 specialisations -------------------------------------------------------------------------
+// With one cell per edge the condensation is  c = r_q0 + r_q1 - (rh/2) r_p,  F_N = r_p,  g = 1/rh:
+// cheap enough to recompute where it is needed, so the per-edge arrays (edge_g, edge_c, edge_fn)
+// and the kernels that fill them disappear from the N == 1 path.
+__global__ void __launch_bounds__(kThreads)
+bif_diag_n1_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n_bif) return;
+  double s = 0.0;
+  for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) s += 1.0 / cell_rh[g.bif_inc[k] >> 1];
+  const int n = t.t_of_bif[i];
+  t.diag0[n] = s;
+  const int pe = t.t_pedge[n];
+  t.tg[n] = pe >= 0 ? 1.0 / cell_rh[pe] : 0.0;
+}
+
+__global__ void __launch_bounds__(kThreads)
+bif_rhs_n1_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* __restrict__ cell_rh,
+                  const double* __restrict__ lam_weight) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n_bif) return;
+  double s = lam_weight ? -lam_weight[i] * r[g.loff + i] : -r[g.loff + i];
+  for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) {
+    const int inc = g.bif_inc[k], e = inc >> 1;
+    const double2 rq = *reinterpret_cast<const double2*>(r + 2 * (size_t)g.edge_slot[e]);
+    const double rp = r[g.poff + e], rh = cell_rh[e];
+    const double gc = ((rq.x + rq.y) - 0.5 * rh * rp) / rh;
+    s += (inc & 1) ? (rp + gc) : -gc;
+  }
+  t.r[t.t_of_bif[i]] = s;
+}
+
+template <bool ADD>
+__global__ void __launch_bounds__(kThreads)
+edge_backsub_n1_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh, const double* __restrict__ r,
+                       double* __restrict__ z) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.E) {
+    const int i = idx - g.E;
+    if (i < g.n_bif) { if (ADD) z[g.loff + i] += t.lam_nat[i]; else z[g.loff + i] = t.lam_nat[i]; }
+    return;
+  }
+  const int e = idx;
+  const int slot = g.edge_slot[e];
+  const int4 uv = g.slot_uvl[slot];
+  const double lu = uv.z >= 0 ? t.lam_nat[uv.z] : 0.0;
+  const double lv = uv.w >= 0 ? t.lam_nat[uv.w] : 0.0;
+  const double2 rq = *reinterpret_cast<const double2*>(r + 2 * (size_t)slot);
+  const double rp = r[g.poff + e], rh = cell_rh[e];
+  const double c = (rq.x + rq.y) - 0.5 * rh * rp;
+  const double q0 = (c + lu - lv) / rh;
+  const double q1 = q0 + rp;
+  const double p = lu + rq.x - rh * (q0 * kThird + q1 * kSixth);
+  double2* zq = reinterpret_cast<double2*>(z + 2 * (size_t)slot);
+  if (ADD) {
+    const double2 o = *zq;
+    *zq = make_double2(o.x + q0, o.y + q1);
+    z[g.poff + e] += p;
+  } else {
+    *zq = make_double2(q0, q1);
+    z[g.poff + e] = p;
+  }
+}
+
 // ---- multi-GPU helpers --------------------------------------------------------------------------
 // shared (replicated) multiplier rows of a vector <-> contiguous buffer for the all-reduce
 __global__ void __launch_bounds__(kThreads)
