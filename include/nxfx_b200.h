@@ -138,6 +138,8 @@ typedef struct {
   int32_t error_if_not_converged;
   int32_t final_residual; /* PREONLY: also evaluate the true residual of the final iterate */
   int32_t reserved;
+  double refine_rtol;     /* PREONLY: a refinement step is skipped (on the device) when the iterate
+                             already satisfies ||b - A x|| <= refine_rtol ||b||; 0 = always refine */
 } nxfx_solve_opts;
 
 #define NXFX_HISTORY_LEN 128

@@ -28,6 +28,7 @@ class SolveOpts(C.Structure):
         ("error_if_not_converged", C.c_int32),
         ("final_residual", C.c_int32),
         ("reserved", C.c_int32),
+        ("refine_rtol", C.c_double),
     ]
 
 

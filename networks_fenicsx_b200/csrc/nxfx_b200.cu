@@ -192,7 +192,7 @@ int do_multi_axpy(nxfx_ctx* ctx, int n, int k, const double* A, size_t stride, c
 
 int ensure_work(nxfx_ctx* ctx, size_t nvec);
 
-int tree_pass(nxfx_ctx* ctx, bool factor) {
+int tree_pass(nxfx_ctx* ctx, bool factor, SkipTest sk = SkipTest{nullptr, 0.0}) {
   auto& s = ctx->tree;
   TreeDev t = make_tree(ctx);
   const int nb = s.n_chunks - 1;  // bottom chunks; the last chunk is the top of the forest
@@ -205,23 +205,23 @@ int tree_pass(nxfx_ctx* ctx, bool factor) {
       unsigned int* fl = ctx->ticket.p + 2;
       unsigned int ep = ++s.epoch;
       int nbv = nb;
-      void* args[] = {&t, &nbv, &tk, &fl, &ep};
+      void* args[] = {&t, &nbv, &tk, &fl, &ep, &sk};
       NXFX_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tree_solve_coop_kernel), dim3(nb), dim3(kTreeThreads),
                                                  args, sizeof(TreeSmem), ctx->stream));
       ctx->launches++;
     } else {
-      NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1);
-      if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1);
+      NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1, sk);
+      if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1, sk);
     }
     return NXFX_OK;
   }
   if (factor) {
-    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<0>, nb, 1024, 0, t, ctx->edge_g.p, 0);
-    NXFX_LAUNCH(ctx, tree_sweep_kernel<0>, 1, 1024, 0, t, ctx->edge_g.p, nb);
+    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<0>, nb, 1024, 0, t, ctx->edge_g.p, 0, sk);
+    NXFX_LAUNCH(ctx, tree_sweep_kernel<0>, 1, 1024, 0, t, ctx->edge_g.p, nb, sk);
   } else {
-    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<1>, nb, 1024, 0, t, ctx->edge_g.p, 0);
-    NXFX_LAUNCH(ctx, tree_sweep_kernel<3>, 1, 1024, 0, t, ctx->edge_g.p, nb);
-    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<2>, nb, 1024, 0, t, ctx->edge_g.p, 0);
+    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<1>, nb, 1024, 0, t, ctx->edge_g.p, 0, sk);
+    NXFX_LAUNCH(ctx, tree_sweep_kernel<3>, 1, 1024, 0, t, ctx->edge_g.p, nb, sk);
+    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<2>, nb, 1024, 0, t, ctx->edge_g.p, 0, sk);
   }
   return NXFX_OK;
 }
@@ -247,7 +247,8 @@ int do_pc_setup(nxfx_ctx* ctx) {
   return NXFX_OK;
 }
 
-int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add = false) {
+int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add = false,
+                SkipTest sk = SkipTest{nullptr, 0.0}) {
   const int n = (int)ctx->ndofs;
   if (add && pc_type != NXFX_PC_NETWORK_SCHUR) {  // generic: z_tmp = P^{-1} r, z += z_tmp
     int rc = ensure_work(ctx, 3);
@@ -273,26 +274,26 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
   if (ctx->N == 1 && ctx->tree.fast_ok) {
     if (ctx->n_bif > 0) {
       NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cell_rh.p,
-                  ctx->lam_weight.p);
-      int rc = tree_pass(ctx, false);
+                  ctx->lam_weight.p, sk);
+      int rc = tree_pass(ctx, false, sk);
       if (rc) return rc;
     }
-    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
-    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z, sk);
+    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z, sk);
     return NXFX_OK;
   }
   NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p,
-              r, ctx->edge_c.p, ctx->edge_fn.p);
+              r, ctx->edge_c.p, ctx->edge_fn.p, sk);
   if (ctx->n_bif > 0) {
     NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r,
-                ctx->edge_g.p, ctx->edge_c.p, ctx->edge_fn.p, ctx->lam_weight.p);
-    int rc = tree_pass(ctx, false);
+                ctx->edge_g.p, ctx->edge_c.p, ctx->edge_fn.p, ctx->lam_weight.p, sk);
+    int rc = tree_pass(ctx, false, sk);
     if (rc) return rc;
   }
   if (add)
-    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z, sk);
   else
-    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z, sk);
   return NXFX_OK;
 }
 
@@ -321,16 +322,20 @@ int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_op
   const int steps = std::max(0, std::min(o->refine_steps, 32));
   if ((rc = do_pc_apply(ctx, o->pc_type, b, x, false))) return rc;
   int nres = 0;
+  // adaptive: a correction is applied only while ||r|| > refine_rtol ||b|| (tested on the device
+  // by the correction kernels themselves: no host round trip)
+  const double rt = o->refine_rtol > 0.0 ? o->refine_rtol : 0.0;
   for (int s = 0; s < steps; ++s) {
     if ((rc = do_residual(ctx, b, x, r, slot(ctx, 2 * nres)))) return rc;
+    SkipTest sk{rt > 0.0 && o->pc_type == NXFX_PC_NETWORK_SCHUR ? slot(ctx, 2 * nres) : nullptr, rt * rt};
     ++nres;
-    if ((rc = do_pc_apply(ctx, o->pc_type, r, x, true))) return rc;
+    if ((rc = do_pc_apply(ctx, o->pc_type, r, x, true, sk))) return rc;
   }
   if (o->final_residual) {
     if ((rc = do_residual(ctx, b, x, r, slot(ctx, 2 * nres)))) return rc;
     ++nres;
   }
-  info->iterations = 1 + steps;
+  info->iterations = 1 + steps;  // corrected below if refinement steps were skipped
   if (nres == 0) {  // nothing measured: plain preconditioner application
     NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     info->rhs_norm = info->residual_norm = -1.0;
@@ -342,6 +347,12 @@ int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_op
   info->rhs_norm = std::sqrt(ctx->scal_h[1]);
   for (int s = 0; s < nres; ++s) push_history(info, std::sqrt(ctx->scal_h[2 * s]));
   info->residual_norm = std::sqrt(ctx->scal_h[2 * (nres - 1)]);
+  if (rt > 0.0) {  // count the corrections that were actually applied
+    int applied = 0;
+    for (int s = 0; s < steps; ++s)
+      if (!(ctx->scal_h[2 * s] <= rt * rt * ctx->scal_h[2 * s + 1])) ++applied;
+    info->iterations = 1 + applied;
+  }
   const double tol = std::max(o->rtol * info->rhs_norm, o->atol);
   info->converged = std::isfinite(info->residual_norm) && info->residual_norm <= tol;
   return NXFX_OK;
@@ -1024,13 +1035,13 @@ int nxfx_pc_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
   TreeDev t = make_tree(ctx);
   const int nb = ctx->tree.n_chunks - 1;
   if (ctx->N == 1) {
-    NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cell_rh.p, ctx->lam_weight.p);
+    NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cell_rh.p, ctx->lam_weight.p, SkipTest{nullptr, 0.0});
   } else {
-    NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p, r, ctx->edge_c.p, ctx->edge_fn.p);
+    NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p, r, ctx->edge_c.p, ctx->edge_fn.p, SkipTest{nullptr, 0.0});
     NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->edge_g.p, ctx->edge_c.p,
-                ctx->edge_fn.p, ctx->lam_weight.p);
+                ctx->edge_fn.p, ctx->lam_weight.p, SkipTest{nullptr, 0.0});
   }
-  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0, SkipTest{nullptr, 0.0});
   NXFX_LAUNCH(ctx, (tree_top_kernel<false, kPartial>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
   return NXFX_OK;
 }
@@ -1043,17 +1054,17 @@ int nxfx_pc_apply_end(nxfx_ctx* ctx, const double* r, double* z, double* buf, in
   TreeDev t = make_tree(ctx);
   const int nb = ctx->tree.n_chunks - 1;
   NXFX_LAUNCH(ctx, (tree_top_kernel<false, kFinish>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
-  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0, SkipTest{nullptr, 0.0});
   const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
   if (ctx->N == 1) {
-    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
-    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z, SkipTest{nullptr, 0.0});
+    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z, SkipTest{nullptr, 0.0});
     return NXFX_OK;
   }
   if (add)
-    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z, SkipTest{nullptr, 0.0});
   else
-    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z, SkipTest{nullptr, 0.0});
   return NXFX_OK;
 }
 

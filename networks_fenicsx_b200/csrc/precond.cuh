@@ -20,6 +20,15 @@
 
 namespace nxfx {
 
+// Adaptive iterative refinement: the kernels of a correction step return at once when the fused
+// norms of the preceding residual kernel show that the iterate is already converged
+// (nrm[0] = ||r||^2, nrm[1] = ||b||^2); nrm == nullptr: unconditional.
+struct SkipTest {
+  const double* nrm;
+  double tol2;
+  __device__ __forceinline__ bool skip() const { return nrm && nrm[0] <= tol2 * nrm[1]; }
+};
+
 struct TreeDev {
   const int32_t* __restrict__ t_of_bif;
   const int32_t* __restrict__ bif_of_t;
@@ -69,7 +78,8 @@ bif_diag_kernel(Net g, TreeDev t, const double* __restrict__ edge_g) {
 // One thread block per chunk; chunk = blockIdx.x + chunk0.
 template <int MODE>
 __global__ void __launch_bounds__(1024)
-tree_sweep_kernel(TreeDev t, const double* __restrict__ edge_g, int chunk0) {
+tree_sweep_kernel(TreeDev t, const double* __restrict__ edge_g, int chunk0, SkipTest sk) {
+  if (sk.skip()) return;
   const int chunk = chunk0 + blockIdx.x;
   const int L0 = t.chunk_lptr[chunk], L1 = t.chunk_lptr[chunk + 1];
   if (MODE == 0 || MODE == 1 || MODE == 3) {
@@ -355,9 +365,10 @@ tree_top_kernel(TreeDev t, int top_chunk, double* buf) {
 
 template <int MODE>
 __global__ void __launch_bounds__(kTreeThreads)
-tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top) {
+tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top, SkipTest sk) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
   TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
+  if (sk.skip()) return;
   if (MODE == kTreeDown) {
     const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
     load_solve_chunk(t, ci, S);
@@ -387,9 +398,11 @@ tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top) {
 
 // single-launch solve: requires all n_bottom blocks to be co-resident (cooperative launch)
 __global__ void __launch_bounds__(kTreeThreads)
-tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch) {
+tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch,
+                       SkipTest sk) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
   TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
+  if (sk.skip()) return;  // uniform over the grid
   const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
   load_children(t, ci, S);
   load_solve_chunk(t, ci, S);
@@ -432,9 +445,9 @@ tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned i
 // Edge condensation: c_e = sum r_q - w.F,  F_N = sum r_p
 __global__ void __launch_bounds__(kThreads)
 edge_condense_kernel(Net g, const double* __restrict__ cell_rh, const double* __restrict__ r,
-                     double* __restrict__ edge_c, double* __restrict__ edge_fn) {
+                     double* __restrict__ edge_c, double* __restrict__ edge_fn, SkipTest sk) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= g.E) return;
+  if (e >= g.E || sk.skip()) return;
   const int N = g.N;
   const double* rq = r + (size_t)g.edge_slot[e] * (N + 1);
   const double* rp = r + g.poff + (size_t)e * N;
@@ -457,9 +470,9 @@ edge_condense_kernel(Net g, const double* __restrict__ cell_rh, const double* __
 __global__ void __launch_bounds__(kThreads)
 bif_rhs_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* __restrict__ edge_g,
                const double* __restrict__ edge_c, const double* __restrict__ edge_fn,
-               const double* __restrict__ lam_weight) {
+               const double* __restrict__ lam_weight, SkipTest sk) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n_bif) return;
+  if (i >= g.n_bif || sk.skip()) return;
   double s = lam_weight ? -lam_weight[i] * r[g.loff + i] : -r[g.loff + i];
   for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) {
     const int inc = g.bif_inc[k], e = inc >> 1;
@@ -475,8 +488,9 @@ template <bool ADD>
 __global__ void __launch_bounds__(kThreads)
 edge_backsub_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh,
                     const double* __restrict__ r, const double* __restrict__ edge_g,
-                    const double* __restrict__ edge_c, double* __restrict__ z) {
+                    const double* __restrict__ edge_c, double* __restrict__ z, SkipTest sk) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sk.skip()) return;
   if (idx >= g.E) {
     const int i = idx - g.E;
     if (i < g.n_bif) { if (ADD) z[g.loff + i] += t.lam_nat[i]; else z[g.loff + i] = t.lam_nat[i]; }
@@ -529,9 +543,9 @@ bif_diag_n1_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh) {
 
 __global__ void __launch_bounds__(kThreads)
 bif_rhs_n1_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* __restrict__ cell_rh,
-                  const double* __restrict__ lam_weight) {
+                  const double* __restrict__ lam_weight, SkipTest sk) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n_bif) return;
+  if (i >= g.n_bif || sk.skip()) return;
   double s = lam_weight ? -lam_weight[i] * r[g.loff + i] : -r[g.loff + i];
   for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) {
     const int inc = g.bif_inc[k], e = inc >> 1;
@@ -546,8 +560,9 @@ bif_rhs_n1_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* 
 template <bool ADD>
 __global__ void __launch_bounds__(kThreads)
 edge_backsub_n1_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh, const double* __restrict__ r,
-                       double* __restrict__ z) {
+                       double* __restrict__ z, SkipTest sk) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sk.skip()) return;
   if (idx >= g.E) {
     const int i = idx - g.E;
     if (i < g.n_bif) { if (ADD) z[g.loff + i] += t.lam_nat[i]; else z[g.loff + i] = t.lam_nat[i]; }

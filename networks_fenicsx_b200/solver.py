@@ -30,7 +30,9 @@ class Solver:
         petsc_options_prefix: Prefix for the options (kept for compatibility).
         petsc_options: Dictionary of PETSc-style options, see :class:`la.KSP`. Extra keys:
             ``nxfx_refine_steps`` (iterative-refinement steps of the direct solve, default 1),
-            ``nxfx_final_residual`` (also evaluate the true residual of the final iterate).
+            ``nxfx_final_residual`` (also evaluate the true residual of the final iterate),
+            ``nxfx_refine_rtol`` (default 1e-13: a refinement step is skipped on the device when the
+            iterate already has that relative residual; 0 = always refine).
         kind: ``None``/``"mpi"`` (monolithic AIJ) or ``"nest"``.
     """
 
@@ -154,6 +156,7 @@ class Solver:
         opts.refine_steps = int(o.get("nxfx_refine_steps", 1))
         opts.error_if_not_converged = int(bool(o.get("ksp_error_if_not_converged", False)))
         opts.final_residual = int(bool(o.get("nxfx_final_residual", False)))
+        opts.refine_rtol = float(o.get("nxfx_refine_rtol", 1e-13))
         return opts
 
     # ---- solve --------------------------------------------------------------------------------

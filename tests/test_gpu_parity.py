@@ -375,3 +375,23 @@ def test_higher_order_matches_low_order_flux():
         out[(fd, pd)] = (q_first, sol[-1].x.array.copy())
     np.testing.assert_allclose(out[(2, 1)][0], out[(1, 0)][0], rtol=1e-8, atol=1e-11)
     np.testing.assert_allclose(out[(2, 1)][1], out[(1, 0)][1], rtol=1e-8, atol=1e-11)
+
+
+def test_adaptive_refinement():
+    """The refinement step is applied only when the first direct solve is not yet at refine_rtol
+    (decided on the device); forcing it gives the same answer."""
+    G = ng.make_tree(9, 4, 5)
+    rng = np.random.default_rng(5)
+    R = 10.0 ** rng.uniform(-4, 4, G.number_of_edges() * 2)  # badly scaled resistances
+    its = {}
+    xs = {}
+    for name, extra in (("default", {}), ("forced", {"nxfx_refine_rtol": 0.0}), ("tight", {"nxfx_refine_rtol": 1e-30}),
+                        ("none", {"nxfx_refine_steps": 0})):
+        opts = {"ksp_type": "preonly", "pc_type": "lu", "nxfx_final_residual": True, **extra}
+        nm, asm, solver, sol, net, A, b = run_case(G, 2, "smallest_last", P_Y, R=R, petsc_options=opts)
+        its[name] = solver.ksp.getIterationNumber()
+        xs[name] = np.concatenate([f.x.array for f in sol])
+        assert helpers.rel_l2(xs[name], net.solve(A, b)) < 1e-8
+        assert solver.info.residual_norm <= 1e-10 * solver.info.rhs_norm
+    assert its["forced"] == 2 and its["tight"] == 2 and its["none"] == 1 and its["default"] in (1, 2)
+    assert helpers.rel_l2(xs["forced"], xs["tight"]) == 0.0
