@@ -166,7 +166,8 @@ def run_gpu(args):
     else:
         nxfx, nm, asm, solver = build_problem(n, local_rank)
         solver.assemble()
-        functions = solver.solve()  # also allocates the pinned result functions
+        functions = solver.create_functions()  # pinned result functions, reused by every e2e step
+        solver.solve(functions)
         n_dofs_total = asm.num_dofs
     dev = nm.device
     n_dofs = asm.num_dofs

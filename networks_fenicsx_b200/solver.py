@@ -80,6 +80,7 @@ class Solver:
             s.lvl_ptr.size, _lib.as_i32p(s.lvl_ptr), s.chord_edge.size, _lib.as_i32p(s.chord_edge),
         )
         self.info = _lib.SolveInfo()
+        self._x_stage = None
 
     @property
     def assembler(self) -> assembly.HydraulicNetworkAssembler:
@@ -104,6 +105,20 @@ class Solver:
     @property
     def ksp(self) -> KSP:
         return self._ksp
+
+    def create_functions(self) -> list[Function]:
+        """Functions ``[flux_color_i ..., pressure, global_flux]`` backed by pinned host memory; pass
+        them to :meth:`solve` to have the solution copied straight into them (no staging copy)."""
+        asm = self.assembler
+        dev = asm.network.device
+        out = []
+        spaces = [*asm.flux_spaces, asm.pressure_space, asm.lm_space]
+        names = [f"flux_color_{i}" for i in range(len(spaces) - 2)] + ["pressure", "global_flux"]
+        for V, name in zip(spaces, names):
+            fn = Function(V, name=name, array=dev.pinned(V.num_dofs))
+            fn._pinned = True
+            out.append(fn)
+        return out
 
     def assemble(self, lhs: bool = True, rhs: bool = True):
         """Zero and re-assemble the system matrix and rhs vector (solver.py:90-101)."""
@@ -172,11 +187,17 @@ class Solver:
         asm = self.assembler
         dev = asm.network.device
         if functions is None:
+            # fresh Functions per call (as the reference does); their arrays are filled from a
+            # pinned staging buffer that the solver keeps, so repeated solves do not pay for
+            # page-locking 8*n_dofs bytes every time
             functions = []
             for i, Vi in enumerate(asm.flux_spaces):
-                functions.append(Function(Vi, name=f"flux_color_{i}", array=dev.pinned(Vi.num_dofs)))
-            functions.append(Function(asm.pressure_space, name="pressure", array=dev.pinned(asm.pressure_space.num_dofs)))
-            functions.append(Function(asm.lm_space, name="global_flux", array=dev.pinned(asm.lm_space.num_dofs)))
+                functions.append(Function(Vi, name=f"flux_color_{i}", array=np.empty(Vi.num_dofs)))
+            functions.append(Function(asm.pressure_space, name="pressure", array=np.empty(asm.pressure_space.num_dofs)))
+            functions.append(Function(asm.lm_space, name="global_flux", array=np.empty(asm.lm_space.num_dofs)))
+            staged = True
+        else:
+            staged = not all(getattr(fn, "_pinned", False) for fn in functions)
         opts = self.solve_options()
         self.info = _lib.SolveInfo()
         self._A._materialise_zero()
@@ -189,17 +210,28 @@ class Solver:
             self._record_info()
         self._x.mark_device_modified()
         # fem.petsc.assign: split the blocked vector into the functions (solver.py:134)
-        off = 0
-        for fn in functions:
-            n = fn.x.array.size
-            if n:
-                dev.call(
-                    "nxfx_memcpy_d2h", C.c_void_p(fn.x.array.ctypes.data),
-                    C.c_void_p(self._x.d.ptr + 8 * off), C.c_size_t(8 * n),
-                )
-            off += n
-        assert off == self._x.n, "functions do not match the block layout"
-        dev.sync()
+        if sum(fn.x.array.size for fn in functions) != self._x.n:
+            raise ValueError("functions do not match the block layout [flux colours, pressure, multipliers]")
+        if staged:
+            if self._x_stage is None:
+                self._x_stage = dev.pinned(self._x.n)
+            self._x.d.download(self._x_stage)  # one D2H, synchronises
+            off = 0
+            for fn in functions:
+                n = fn.x.array.size
+                np.copyto(fn.x.array, self._x_stage[off:off + n])
+                off += n
+        else:  # caller-provided pinned arrays (Solver.create_functions): D2H straight into them
+            off = 0
+            for fn in functions:
+                n = fn.x.array.size
+                if n:
+                    dev.call(
+                        "nxfx_memcpy_d2h", C.c_void_p(fn.x.array.ctypes.data),
+                        C.c_void_p(self._x.d.ptr + 8 * off), C.c_size_t(8 * n),
+                    )
+                off += n
+            dev.sync()
         return functions
 
     def _record_info(self):
