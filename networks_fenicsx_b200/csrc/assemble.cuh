@@ -79,17 +79,10 @@ struct VertexRec {
 };
 
 // one 32-byte sector per vertex: coordinates and the boundary pressure travel together
-// (sm_100a: one 256-bit load per record with NXFX_V256, which also allows the L2 evict_last hint)
 __device__ __forceinline__ VertexRec load_vertex(const double2* __restrict__ x2, int v) {
   const double2* p = x2 + 2 * (size_t)v;
-#ifdef NXFX_V256
-  double ax, ay, bx, by;
-  asm volatile("ld.global.L2::evict_last.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(ax), "=d"(ay), "=d"(bx), "=d"(by) : "l"(p));
-  return VertexRec{ax, ay, bx, by};
-#else
   const double2 a = __ldg(p), b = __ldg(p + 1);
   return VertexRec{a.x, a.y, b.x, b.y};
-#endif
 }
 
 __device__ __forceinline__ double seg_length(const VertexRec& v0, const VertexRec& v1) {
@@ -346,15 +339,9 @@ constexpr int kLamRows = 256;
 
 // The value / rhs streams are written once and not re-read by this kernel: streaming (evict-first)
 // stores keep them from pushing the vertex records out of L2.
-#ifndef NXFX_ASM_NOHINT
 #define NXFX_ST2(ptr, v) __stcs((ptr), (v))
 #define NXFX_ST1(ptr, v) __stcs((ptr), (v))
 #define NXFX_LDS(ptr) __ldcs(ptr)
-#else
-#define NXFX_ST2(ptr, v) (*(ptr) = (v))
-#define NXFX_ST1(ptr, v) (*(ptr) = (v))
-#define NXFX_LDS(ptr) (*(ptr))
-#endif
 
 template <bool ACC>
 __device__ __forceinline__ void store_pair(double* __restrict__ vals, size_t idx, double v0, double v1) {

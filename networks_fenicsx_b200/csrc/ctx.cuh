@@ -42,7 +42,6 @@ struct TreeSchedule {
   DevBuf<int32_t> bif_of_t, chunk_desc;
   DevBuf<double> lam_nat;
   DevBuf<int32_t> t_of_bif, t_parent, t_pedge, t_cptr, t_cidx, chunk_lptr, lvl_ptr, chord_edge;
-  std::vector<int32_t> chunk_lptr_h, lvl_ptr_h;
   // numeric
   DevBuf<double> diag0, tg, d, gd, r, lam;  // schedule order
   bool fast_ok = false;                       // every chunk fits the shared-memory sweep kernel

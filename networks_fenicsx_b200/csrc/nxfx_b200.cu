@@ -315,7 +315,6 @@ void push_history(nxfx_solve_info* info, double v) {
 // opts->final_residual is set, otherwise the residual of the iterate BEFORE the last correction
 // (an upper estimate; KSPPREONLY itself computes none).
 int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts* o, nxfx_solve_info* info) {
-  const int n = (int)ctx->ndofs;
   int rc = ensure_work(ctx, 3);
   if (rc) return rc;
   double* r = ctx->work.p;
@@ -984,10 +983,8 @@ int nxfx_set_shared(nxfx_ctx* ctx, int32_t n_shared, const int32_t* shared_lm, c
 }
 
 static int dist_ready(nxfx_ctx* ctx, const double* buf) {
-  NXFX_REQUIRE(ctx, ctx->tree.set && ctx->tree.fast_ok && ctx->tree.n_chunks >= 1 && buf, "needs a shared-memory tree schedule and a buffer");
-  auto& s = ctx->tree;
-  const int top_nodes = s.n_lvl_ptr > 0 ? ctx->n_bif - 0 : 0;
-  (void)top_nodes;
+  NXFX_REQUIRE(ctx, ctx->tree.set && ctx->tree.fast_ok && ctx->tree.n_chunks >= 1 && buf,
+               "needs a tree schedule that fits the shared-memory sweeps and a buffer");
   return NXFX_OK;
 }
 

@@ -1,11 +1,13 @@
 // CSR SpMV and fused vector kernels for the Krylov solve (solver.py:127 replaces KSPSolve).
 //
-// SpMV is the CSR-stream form: a block owns kTileRows consecutive rows, streams the tile's
-// (value, column) pairs from HBM with fully coalesced loads (8 independent loads per thread in
-// flight), gathers x from L2 (x is 8*n_dofs bytes, far below the 126 MB L2), parks the products
-// in shared memory and reduces each row sequentially in ascending column order.  The row sum is
-// therefore deterministic and bit-identical to a sequential CSR product (mul then add, no FMA).
-// The residual variant fuses r = b - A x and the block partial of ||r||^2 into the same pass.
+// A block owns tiles of kTileRows consecutive rows: the tile's (value, column) pairs are streamed
+// from HBM, x is gathered from L2 (x is 8*n_dofs bytes, far below the 126 MB L2), the products are
+// parked in shared memory and every row is reduced sequentially in ascending column order.  The
+// row sum is therefore deterministic and bit-identical to a sequential CSR product (mul then add,
+// no FMA).  MODE 1 fuses r = b - A x with the block partials of ||r||^2 and ||b||^2.
+//   spmv_pipe_kernel  persistent blocks, TMA bulk copies (cp.async.bulk) + mbarrier pipeline,
+//                     L2 evict-first hint on the matrix stream -- the production kernel;
+//   spmv_kernel       plain loads, any tile size -- fallback for very long rows.
 #pragma once
 
 #include "ctx.cuh"
@@ -157,13 +159,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
 // streaming variant: the matrix is read once per product, so its lines are marked evict-first in
 // L2 and do not push out the x vector the gathers keep re-using
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
@@ -221,9 +216,7 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-#ifndef NXFX_SPMV_NOHINT
   const uint64_t stream_policy = l2_evict_first_policy();
-#endif
   auto issue = [&](int tile, int s) {
     const int r0 = tile * kTileRows;
     const int nr = min(kTileRows, n - r0);
@@ -232,19 +225,11 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
     const int cnt4 = ((se + 3) & ~3) - s4;
     const uint32_t rbytes = (uint32_t)(((nr + 1) * 4 + 15) & ~15);
     mbar_expect_tx(full + s, (uint32_t)cnt4 * 12u + rbytes);
-#ifndef NXFX_SPMV_NOHINT
     if (cnt4 > 0) {
       bulk_g2s_stream(st[s].vals, vals + s4, (uint32_t)cnt4 * 8u, full + s, stream_policy);
       bulk_g2s_stream(st[s].cols, colidx + s4, (uint32_t)cnt4 * 4u, full + s, stream_policy);
     }
     bulk_g2s_stream(st[s].rows, rowptr + r0, rbytes, full + s, stream_policy);
-#else
-    if (cnt4 > 0) {
-      bulk_g2s(st[s].vals, vals + s4, (uint32_t)cnt4 * 8u, full + s);
-      bulk_g2s(st[s].cols, colidx + s4, (uint32_t)cnt4 * 4u, full + s);
-    }
-    bulk_g2s(st[s].rows, rowptr + r0, rbytes, full + s);
-#endif
   };
   if (tid == 0) {
     for (int k = 0; k < kStages - 1; ++k) {
@@ -296,16 +281,11 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
       const int rs = S.rows[tid] - base + off, re = S.rows[tid + 1] - base + off;
       double acc = 0.0;
       for (int k = rs; k < re; ++k) acc = __dadd_rn(acc, S.vals[k]);
-#ifdef NXFX_Y_STCS
-#define NXFX_YST(p, v) __stcs((p), (v))
-#else
-#define NXFX_YST(p, v) (*(p) = (v))
-#endif
       if (MODE == 0) {
-        NXFX_YST(y + r0 + tid, acc);
+        y[r0 + tid] = acc;
       } else {
         const double r = __dsub_rn(bi, acc);
-        NXFX_YST(y + r0 + tid, r);
+        y[r0 + tid] = r;
         nrm += r * r;
         nrb += bi * bi;
       }
