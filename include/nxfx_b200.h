@@ -138,8 +138,8 @@ typedef struct {
   int32_t error_if_not_converged;
   int32_t final_residual; /* PREONLY: also evaluate the true residual of the final iterate */
   int32_t reserved;
-  double refine_rtol;     /* PREONLY: a refinement step is skipped (on the device) when the iterate
-                             already satisfies ||b - A x|| <= refine_rtol ||b||; 0 = always refine */
+  double refine_rtol;     /* PREONLY: refinement stops as soon as ||b - A x|| <= refine_rtol ||b||;
+                             0 = always apply refine_steps corrections */
 } nxfx_solve_opts;
 
 #define NXFX_HISTORY_LEN 128
@@ -218,7 +218,11 @@ int nxfx_assemble_generic(nxfx_ctx* ctx, const double* R_cell_d, double R_const,
  *   nxfx_pc_apply_end    <- all-reduced buf: top solve, back-substitution; z = or += P^{-1} r
  *   nxfx_pack_shared / nxfx_unpack_shared  shared multiplier rows of a vector <-> buf (after
  *                        y = A x these rows are partial sums)
- *   nxfx_norm2_owned     out_d[0] = sum of squares over the entries this rank owns (async)     */
+ *   nxfx_norm2_owned     out_d[0] = sum of squares over the entries this rank owns (async)
+ *   nxfx_residual_partial  r = b - A x (local part) and buf = [shared rows of r | partial ||r||^2
+ *                        over the non-shared owned rows | owned ||b||^2]  (n_shared + 2 doubles)
+ *   nxfx_residual_finish <- all-reduced buf: shared rows written back to r, nrm_out_d = [||r||^2,
+ *                        ||b||^2], identical on every rank                                    */
 int nxfx_set_shared(nxfx_ctx* ctx, int32_t n_shared, const int32_t* shared_lm_h,
                     const double* lam_weight_h);
 int nxfx_top_size(nxfx_ctx* ctx, int32_t* n_top);
@@ -229,6 +233,9 @@ int nxfx_pc_apply_end(nxfx_ctx* ctx, const double* r_d, double* z_d, double* buf
 int nxfx_pack_shared(nxfx_ctx* ctx, const double* v_d, double* buf_d);
 int nxfx_unpack_shared(nxfx_ctx* ctx, const double* buf_d, double* v_d);
 int nxfx_norm2_owned(nxfx_ctx* ctx, const double* v_d, double* out_d);
+int nxfx_residual_partial(nxfx_ctx* ctx, const double* b_d, const double* x_d, double* r_d,
+                          double* buf_d);
+int nxfx_residual_finish(nxfx_ctx* ctx, const double* buf_d, double* r_d, double* nrm_out_d);
 
 /* ---- post-processing ----------------------------------------------------------------------- *
  * Replaces Function.interpolate into the DG space in extract_global_flux: post_processing.py:36-51.

@@ -121,6 +121,8 @@ SIGNATURES = {
     "nxfx_pack_shared": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nxfx_unpack_shared": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nxfx_norm2_owned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nxfx_residual_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nxfx_residual_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nxfx_global_flux": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

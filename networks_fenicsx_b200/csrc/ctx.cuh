@@ -86,7 +86,7 @@ struct nxfx_ctx {
   // multi-GPU: replicated multipliers
   int32_t n_shared = 0;
   nxfx::DevBuf<int32_t> shared_lm;
-  nxfx::DevBuf<double> lam_weight;
+  nxfx::DevBuf<double> lam_weight, lam_nonshared;
   // e2e staging
   nxfx::DevBuf<double> e2e_pbc, e2e_b, e2e_x;
 };

@@ -192,7 +192,7 @@ int do_multi_axpy(nxfx_ctx* ctx, int n, int k, const double* A, size_t stride, c
 
 int ensure_work(nxfx_ctx* ctx, size_t nvec);
 
-int tree_pass(nxfx_ctx* ctx, bool factor, SkipTest sk = SkipTest{nullptr, 0.0}) {
+int tree_pass(nxfx_ctx* ctx, bool factor) {
   auto& s = ctx->tree;
   TreeDev t = make_tree(ctx);
   const int nb = s.n_chunks - 1;  // bottom chunks; the last chunk is the top of the forest
@@ -205,23 +205,23 @@ int tree_pass(nxfx_ctx* ctx, bool factor, SkipTest sk = SkipTest{nullptr, 0.0}) 
       unsigned int* fl = ctx->ticket.p + 2;
       unsigned int ep = ++s.epoch;
       int nbv = nb;
-      void* args[] = {&t, &nbv, &tk, &fl, &ep, &sk};
+      void* args[] = {&t, &nbv, &tk, &fl, &ep};
       NXFX_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tree_solve_coop_kernel), dim3(nb), dim3(kTreeThreads),
                                                  args, sizeof(TreeSmem), ctx->stream));
       ctx->launches++;
     } else {
-      NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1, sk);
-      if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1, sk);
+      NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1);
+      if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1);
     }
     return NXFX_OK;
   }
   if (factor) {
-    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<0>, nb, 1024, 0, t, ctx->edge_g.p, 0, sk);
-    NXFX_LAUNCH(ctx, tree_sweep_kernel<0>, 1, 1024, 0, t, ctx->edge_g.p, nb, sk);
+    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<0>, nb, 1024, 0, t, ctx->edge_g.p, 0);
+    NXFX_LAUNCH(ctx, tree_sweep_kernel<0>, 1, 1024, 0, t, ctx->edge_g.p, nb);
   } else {
-    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<1>, nb, 1024, 0, t, ctx->edge_g.p, 0, sk);
-    NXFX_LAUNCH(ctx, tree_sweep_kernel<3>, 1, 1024, 0, t, ctx->edge_g.p, nb, sk);
-    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<2>, nb, 1024, 0, t, ctx->edge_g.p, 0, sk);
+    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<1>, nb, 1024, 0, t, ctx->edge_g.p, 0);
+    NXFX_LAUNCH(ctx, tree_sweep_kernel<3>, 1, 1024, 0, t, ctx->edge_g.p, nb);
+    if (nb > 0) NXFX_LAUNCH(ctx, tree_sweep_kernel<2>, nb, 1024, 0, t, ctx->edge_g.p, 0);
   }
   return NXFX_OK;
 }
@@ -247,8 +247,7 @@ int do_pc_setup(nxfx_ctx* ctx) {
   return NXFX_OK;
 }
 
-int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add = false,
-                SkipTest sk = SkipTest{nullptr, 0.0}) {
+int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add = false) {
   const int n = (int)ctx->ndofs;
   if (add && pc_type != NXFX_PC_NETWORK_SCHUR) {  // generic: z_tmp = P^{-1} r, z += z_tmp
     int rc = ensure_work(ctx, 3);
@@ -274,26 +273,26 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
   if (ctx->N == 1 && ctx->tree.fast_ok) {
     if (ctx->n_bif > 0) {
       NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cell_rh.p,
-                  ctx->lam_weight.p, sk);
-      int rc = tree_pass(ctx, false, sk);
+                  ctx->lam_weight.p);
+      int rc = tree_pass(ctx, false);
       if (rc) return rc;
     }
-    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z, sk);
-    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z, sk);
+    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
     return NXFX_OK;
   }
   NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p,
-              r, ctx->edge_c.p, ctx->edge_fn.p, sk);
+              r, ctx->edge_c.p, ctx->edge_fn.p);
   if (ctx->n_bif > 0) {
     NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r,
-                ctx->edge_g.p, ctx->edge_c.p, ctx->edge_fn.p, ctx->lam_weight.p, sk);
-    int rc = tree_pass(ctx, false, sk);
+                ctx->edge_g.p, ctx->edge_c.p, ctx->edge_fn.p, ctx->lam_weight.p);
+    int rc = tree_pass(ctx, false);
     if (rc) return rc;
   }
   if (add)
-    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z, sk);
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
   else
-    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z, sk);
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
   return NXFX_OK;
 }
 
@@ -309,49 +308,41 @@ void push_history(nxfx_solve_info* info, double v) {
   if (info->history_len < NXFX_HISTORY_LEN) info->history[info->history_len++] = v;
 }
 
-// x = P^{-1} b followed by `refine_steps` steps of iterative refinement x += P^{-1}(b - A x); the
-// residual kernel also returns ||b||^2, the back-substitution updates x in place; one sync at the
-// end.  The reported residual is the last one computed: the true final residual when
-// opts->final_residual is set, otherwise the residual of the iterate BEFORE the last correction
-// (an upper estimate; KSPPREONLY itself computes none).
+// x = P^{-1} b, then iterative refinement x += P^{-1}(b - A x) while the residual (evaluated with
+// the fused norms of the SpMV kernel) exceeds refine_rtol ||b||, at most refine_steps corrections.
+// The decision is taken on the host after the one synchronisation the solve needs anyway to return
+// its norms: the common case (first solve already converged) costs one SpMV and no extra launch.
+// refine_rtol = 0 forces every allowed correction.  The reported residual is the last one computed;
+// final_residual adds an evaluation after the last correction.
 int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts* o, nxfx_solve_info* info) {
   int rc = ensure_work(ctx, 3);
   if (rc) return rc;
   double* r = ctx->work.p;
   const int steps = std::max(0, std::min(o->refine_steps, 32));
   if ((rc = do_pc_apply(ctx, o->pc_type, b, x, false))) return rc;
-  int nres = 0;
-  // adaptive: a correction is applied only while ||r|| > refine_rtol ||b|| (tested on the device
-  // by the correction kernels themselves: no host round trip)
-  const double rt = o->refine_rtol > 0.0 ? o->refine_rtol : 0.0;
-  for (int s = 0; s < steps; ++s) {
-    if ((rc = do_residual(ctx, b, x, r, slot(ctx, 2 * nres)))) return rc;
-    SkipTest sk{rt > 0.0 && o->pc_type == NXFX_PC_NETWORK_SCHUR ? slot(ctx, 2 * nres) : nullptr, rt * rt};
-    ++nres;
-    if ((rc = do_pc_apply(ctx, o->pc_type, r, x, true, sk))) return rc;
-  }
-  if (o->final_residual) {
-    if ((rc = do_residual(ctx, b, x, r, slot(ctx, 2 * nres)))) return rc;
-    ++nres;
-  }
-  info->iterations = 1 + steps;  // corrected below if refinement steps were skipped
-  if (nres == 0) {  // nothing measured: plain preconditioner application
+  info->iterations = 1;
+  if (steps == 0 && !o->final_residual) {  // plain preconditioner application, nothing measured
     NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     info->rhs_norm = info->residual_norm = -1.0;
     info->converged = 1;
     return NXFX_OK;
   }
-  NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, slot(ctx, 0), 2 * nres * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  info->rhs_norm = std::sqrt(ctx->scal_h[1]);
-  for (int s = 0; s < nres; ++s) push_history(info, std::sqrt(ctx->scal_h[2 * s]));
-  info->residual_norm = std::sqrt(ctx->scal_h[2 * (nres - 1)]);
-  if (rt > 0.0) {  // count the corrections that were actually applied
-    int applied = 0;
-    for (int s = 0; s < steps; ++s)
-      if (!(ctx->scal_h[2 * s] <= rt * rt * ctx->scal_h[2 * s + 1])) ++applied;
-    info->iterations = 1 + applied;
+  const double rt = o->refine_rtol > 0.0 ? o->refine_rtol : 0.0;
+  int applied = 0;
+  while (true) {
+    if ((rc = do_residual(ctx, b, x, r, slot(ctx, 0)))) return rc;
+    NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, slot(ctx, 0), 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    info->rhs_norm = std::sqrt(ctx->scal_h[1]);
+    info->residual_norm = std::sqrt(ctx->scal_h[0]);
+    push_history(info, info->residual_norm);
+    const bool good = std::isfinite(info->residual_norm) && info->residual_norm <= rt * info->rhs_norm;
+    if (applied >= steps || (good && rt > 0.0) || !std::isfinite(info->residual_norm)) break;
+    if ((rc = do_pc_apply(ctx, o->pc_type, r, x, true))) return rc;
+    ++applied;
+    if (applied >= steps && !o->final_residual) break;  // residual of the iterate before the last correction
   }
+  info->iterations = 1 + applied;
   const double tol = std::max(o->rtol * info->rhs_norm, o->atol);
   info->converged = std::isfinite(info->residual_norm) && info->residual_norm <= tol;
   return NXFX_OK;
@@ -602,6 +593,7 @@ int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gd
   ctx->n_shared = 0;
   ctx->shared_lm.release();
   ctx->lam_weight.release();
+  ctx->lam_nonshared.release();
   ctx->tree.set = false;
   ctx->n_nodes = n_nodes; ctx->E = n_edges; ctx->gdim = gdim; ctx->N = N; ctx->n_bif = n_bif;
   ctx->n_inc = n_inc; ctx->nv = nv; ctx->nc = nc; ctx->nq = nq; ctx->poff = nq; ctx->loff = nq + nc;
@@ -977,6 +969,10 @@ int nxfx_set_shared(nxfx_ctx* ctx, int32_t n_shared, const int32_t* shared_lm, c
   int rc;
   if ((rc = upload(ctx, ctx->shared_lm, shared_lm, (size_t)n_shared))) return rc;
   if ((rc = upload(ctx, ctx->lam_weight, lam_weight, (size_t)ctx->n_bif))) return rc;
+  std::vector<double> nonshared((size_t)ctx->n_bif);
+  for (int32_t i = 0; i < ctx->n_bif; ++i) nonshared[i] = lam_weight[i];
+  for (int32_t i = 0; i < n_shared; ++i) nonshared[shared_lm[i]] = 0.0;
+  if ((rc = upload(ctx, ctx->lam_nonshared, nonshared.data(), (size_t)ctx->n_bif))) return rc;
   NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->n_shared = n_shared;
   return NXFX_OK;
@@ -1032,13 +1028,13 @@ int nxfx_pc_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
   TreeDev t = make_tree(ctx);
   const int nb = ctx->tree.n_chunks - 1;
   if (ctx->N == 1) {
-    NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cell_rh.p, ctx->lam_weight.p, SkipTest{nullptr, 0.0});
+    NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cell_rh.p, ctx->lam_weight.p);
   } else {
-    NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p, r, ctx->edge_c.p, ctx->edge_fn.p, SkipTest{nullptr, 0.0});
+    NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p, r, ctx->edge_c.p, ctx->edge_fn.p);
     NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->edge_g.p, ctx->edge_c.p,
-                ctx->edge_fn.p, ctx->lam_weight.p, SkipTest{nullptr, 0.0});
+                ctx->edge_fn.p, ctx->lam_weight.p);
   }
-  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0, SkipTest{nullptr, 0.0});
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
   NXFX_LAUNCH(ctx, (tree_top_kernel<false, kPartial>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
   return NXFX_OK;
 }
@@ -1051,17 +1047,17 @@ int nxfx_pc_apply_end(nxfx_ctx* ctx, const double* r, double* z, double* buf, in
   TreeDev t = make_tree(ctx);
   const int nb = ctx->tree.n_chunks - 1;
   NXFX_LAUNCH(ctx, (tree_top_kernel<false, kFinish>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
-  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0, SkipTest{nullptr, 0.0});
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
   const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
   if (ctx->N == 1) {
-    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z, SkipTest{nullptr, 0.0});
-    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z, SkipTest{nullptr, 0.0});
+    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
     return NXFX_OK;
   }
   if (add)
-    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z, SkipTest{nullptr, 0.0});
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
   else
-    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z, SkipTest{nullptr, 0.0});
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
   return NXFX_OK;
 }
 
@@ -1078,6 +1074,25 @@ int nxfx_unpack_shared(nxfx_ctx* ctx, const double* buf, double* v) {
   if (ctx->n_shared > 0)
     NXFX_LAUNCH(ctx, unpack_shared_kernel, (int)cdiv(ctx->n_shared, kThreads), kThreads, 0, ctx->n_shared, (int)ctx->loff,
                 ctx->shared_lm.p, buf, v);
+  return NXFX_OK;
+}
+
+int nxfx_residual_partial(nxfx_ctx* ctx, const double* b, const double* x, double* r, double* buf) {
+  if (!ctx || !b || !x || !r || !buf) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_pattern && ctx->lam_nonshared.p, "nxfx_set_shared has not been called");
+  int rc = do_residual(ctx, b, x, r, slot(ctx, 0));
+  if (rc) return rc;
+  if ((rc = nxfx_pack_shared(ctx, r, buf))) return rc;
+  const int n = (int)ctx->ndofs;
+  NXFX_LAUNCH(ctx, weighted_norm2_pair_kernel, vec_grid(ctx, n), kThreads, 0, n, (int)ctx->loff, r, ctx->lam_nonshared.p,
+              b, ctx->lam_weight.p, ctx->scal.p, ctx->ticket.p, buf + ctx->n_shared);
+  return NXFX_OK;
+}
+
+int nxfx_residual_finish(nxfx_ctx* ctx, const double* buf, double* r, double* nrm_out) {
+  if (!ctx || !buf || !r || !nrm_out) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->lam_nonshared.p, "nxfx_set_shared has not been called");
+  NXFX_LAUNCH(ctx, residual_finish_kernel, 1, kThreads, 0, ctx->n_shared, (int)ctx->loff, ctx->shared_lm.p, buf, r, nrm_out);
   return NXFX_OK;
 }
 

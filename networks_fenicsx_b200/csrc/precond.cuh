@@ -17,17 +17,9 @@
 #pragma once
 
 #include "assemble.cuh"
+#include "spmv.cuh"
 
 namespace nxfx {
-
-// Adaptive iterative refinement: the kernels of a correction step return at once when the fused
-// norms of the preceding residual kernel show that the iterate is already converged
-// (nrm[0] = ||r||^2, nrm[1] = ||b||^2); nrm == nullptr: unconditional.
-struct SkipTest {
-  const double* nrm;
-  double tol2;
-  __device__ __forceinline__ bool skip() const { return nrm && nrm[0] <= tol2 * nrm[1]; }
-};
 
 struct TreeDev {
   const int32_t* __restrict__ t_of_bif;
@@ -78,8 +70,7 @@ bif_diag_kernel(Net g, TreeDev t, const double* __restrict__ edge_g) {
 // One thread block per chunk; chunk = blockIdx.x + chunk0.
 template <int MODE>
 __global__ void __launch_bounds__(1024)
-tree_sweep_kernel(TreeDev t, const double* __restrict__ edge_g, int chunk0, SkipTest sk) {
-  if (sk.skip()) return;
+tree_sweep_kernel(TreeDev t, const double* __restrict__ edge_g, int chunk0) {
   const int chunk = chunk0 + blockIdx.x;
   const int L0 = t.chunk_lptr[chunk], L1 = t.chunk_lptr[chunk + 1];
   if (MODE == 0 || MODE == 1 || MODE == 3) {
@@ -365,10 +356,9 @@ tree_top_kernel(TreeDev t, int top_chunk, double* buf) {
 
 template <int MODE>
 __global__ void __launch_bounds__(kTreeThreads)
-tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top, SkipTest sk) {
+tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
   TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
-  if (sk.skip()) return;
   if (MODE == kTreeDown) {
     const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
     load_solve_chunk(t, ci, S);
@@ -398,11 +388,9 @@ tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top, Ski
 
 // single-launch solve: requires all n_bottom blocks to be co-resident (cooperative launch)
 __global__ void __launch_bounds__(kTreeThreads)
-tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch,
-                       SkipTest sk) {
+tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
   TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
-  if (sk.skip()) return;  // uniform over the grid
   const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
   load_children(t, ci, S);
   load_solve_chunk(t, ci, S);
@@ -445,9 +433,9 @@ tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned i
 // Edge condensation: c_e = sum r_q - w.F,  F_N = sum r_p
 __global__ void __launch_bounds__(kThreads)
 edge_condense_kernel(Net g, const double* __restrict__ cell_rh, const double* __restrict__ r,
-                     double* __restrict__ edge_c, double* __restrict__ edge_fn, SkipTest sk) {
+                     double* __restrict__ edge_c, double* __restrict__ edge_fn) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= g.E || sk.skip()) return;
+  if (e >= g.E) return;
   const int N = g.N;
   const double* rq = r + (size_t)g.edge_slot[e] * (N + 1);
   const double* rp = r + g.poff + (size_t)e * N;
@@ -470,9 +458,9 @@ edge_condense_kernel(Net g, const double* __restrict__ cell_rh, const double* __
 __global__ void __launch_bounds__(kThreads)
 bif_rhs_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* __restrict__ edge_g,
                const double* __restrict__ edge_c, const double* __restrict__ edge_fn,
-               const double* __restrict__ lam_weight, SkipTest sk) {
+               const double* __restrict__ lam_weight) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n_bif || sk.skip()) return;
+  if (i >= g.n_bif) return;
   double s = lam_weight ? -lam_weight[i] * r[g.loff + i] : -r[g.loff + i];
   for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) {
     const int inc = g.bif_inc[k], e = inc >> 1;
@@ -488,9 +476,8 @@ template <bool ADD>
 __global__ void __launch_bounds__(kThreads)
 edge_backsub_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh,
                     const double* __restrict__ r, const double* __restrict__ edge_g,
-                    const double* __restrict__ edge_c, double* __restrict__ z, SkipTest sk) {
+                    const double* __restrict__ edge_c, double* __restrict__ z) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (sk.skip()) return;
   if (idx >= g.E) {
     const int i = idx - g.E;
     if (i < g.n_bif) { if (ADD) z[g.loff + i] += t.lam_nat[i]; else z[g.loff + i] = t.lam_nat[i]; }
@@ -543,9 +530,9 @@ bif_diag_n1_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh) {
 
 __global__ void __launch_bounds__(kThreads)
 bif_rhs_n1_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* __restrict__ cell_rh,
-                  const double* __restrict__ lam_weight, SkipTest sk) {
+                  const double* __restrict__ lam_weight) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n_bif || sk.skip()) return;
+  if (i >= g.n_bif) return;
   double s = lam_weight ? -lam_weight[i] * r[g.loff + i] : -r[g.loff + i];
   for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) {
     const int inc = g.bif_inc[k], e = inc >> 1;
@@ -560,9 +547,8 @@ bif_rhs_n1_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* 
 template <bool ADD>
 __global__ void __launch_bounds__(kThreads)
 edge_backsub_n1_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh, const double* __restrict__ r,
-                       double* __restrict__ z, SkipTest sk) {
+                       double* __restrict__ z) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (sk.skip()) return;
   if (idx >= g.E) {
     const int i = idx - g.E;
     if (i < g.n_bif) { if (ADD) z[g.loff + i] += t.lam_nat[i]; else z[g.loff + i] = t.lam_nat[i]; }
@@ -603,6 +589,29 @@ unpack_shared_kernel(int n_shared, int loff, const int32_t* __restrict__ shared_
                      const double* __restrict__ buf, double* __restrict__ v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_shared) v[loff + shared_lm[i]] = buf[i];
+}
+
+// After the all-reduce of [shared rows of r | partial ||r||^2 | ||b||^2]: write the reduced shared
+// rows back into r and finish the norms (identical on every rank).  One block.
+__global__ void __launch_bounds__(kThreads)
+residual_finish_kernel(int n_shared, int loff, const int32_t* __restrict__ shared_lm,
+                       const double* __restrict__ buf, double* __restrict__ r, double* __restrict__ nrm_out) {
+  __shared__ double red[kThreads / 32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_shared; i += blockDim.x) {
+    const double v = buf[i];
+    r[loff + shared_lm[i]] = v;
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = buf[n_shared];
+    for (int w = 0; w < kThreads / 32; ++w) s += red[w];
+    nrm_out[0] = s;
+    nrm_out[1] = buf[n_shared + 1];
+  }
 }
 
 // z = D^{-1} r on flux rows (D = diag of the mass block), identity elsewhere

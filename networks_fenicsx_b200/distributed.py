@@ -154,7 +154,7 @@ class DistributedSolver:
         self.dev.call("nxfx_set_shared", shared.size, _lib.as_i32p(shared), _lib.as_f64p(weight))
         cuda = torch.device("cuda", device)
         self._top = torch.zeros(2 * max(part.n_top, 1), dtype=torch.float64, device=cuda)
-        self._sh = torch.zeros(max(shared.size, 1), dtype=torch.float64, device=cuda)
+        self._sh = torch.zeros(shared.size + 2, dtype=torch.float64, device=cuda)  # halo rows + 2 norm partials
         self._nrm = torch.zeros(2 * 40, dtype=torch.float64, device=cuda)
         self._r = self.dev.empty(self.assembler.num_dofs)
         self.n_dofs_global = int(self._allreduce_scalar(self._owned_dofs()))
@@ -181,11 +181,13 @@ class DistributedSolver:
         self._dist.all_reduce(self._top[: self.part.n_top], group=self._group)
         self.dev.call("nxfx_pc_apply_end", r_ptr, z_ptr, top, add)
 
-    def solve(self, refine_steps: int = 1, final_residual: bool = False):
-        """x = P^{-1} b, then ``refine_steps`` refinement steps.  Returns the list of global
-        relative residual norms that were evaluated (the last one belongs to the iterate before the
-        last correction unless ``final_residual``)."""
-        dev, C = self.dev, self._C
+    def solve(self, refine_steps: int = 1, final_residual: bool = False, refine_rtol: float = 1e-13):
+        """x = P^{-1} b, then iterative refinement while ``||b - A x|| > refine_rtol ||b||`` (at most
+        ``refine_steps`` corrections; the all-reduced norms are identical on every rank, so all
+        ranks take the same decision).  Returns the global relative residual norms that were
+        evaluated.  Collectives: 1 (setup) + 1 per preconditioner application + 1 per residual
+        (halo rows and norm partials travel in one buffer)."""
+        dev = self.dev
         b = self.solver.b.device_ptr()
         x = self.solver.x.device_ptr_overwrite()
         top = self._ptr(self._top)
@@ -193,34 +195,34 @@ class DistributedSolver:
         self._dist.all_reduce(self._top, group=self._group)
         dev.call("nxfx_pc_setup_end", top)
         self._apply(b, x, 0)
-        n_eval = 0
-        for s in range(refine_steps + (1 if final_residual else 0)):
-            self._residual(b, x, n_eval)
-            n_eval += 1
-            if s < refine_steps:
-                self._apply(self._r.c_ptr, x, 1)
-        self.solver.x.mark_device_modified()
-        if n_eval:
-            self._dist.all_reduce(self._nrm[: 2 * n_eval], group=self._group)
-            vals = self._nrm[: 2 * n_eval].cpu().numpy()
+        self.history = []
+        applied = 0
+        while refine_steps > 0 or final_residual:
+            self._residual(b, x, 0)
+            vals = self._nrm[:2].cpu().numpy()  # synchronises; identical on all ranks
             self.rhs_norm = float(np.sqrt(vals[1]))
-            self.history = [float(np.sqrt(vals[2 * k]) / self.rhs_norm) for k in range(n_eval)]
-        else:
+            rel = float(np.sqrt(vals[0]) / self.rhs_norm) if self.rhs_norm > 0 else 0.0
+            self.history.append(rel)
+            if applied >= refine_steps or (refine_rtol > 0 and rel <= refine_rtol) or not np.isfinite(rel):
+                break
+            self._apply(self._r.c_ptr, x, 1)
+            applied += 1
+            if applied >= refine_steps and not final_residual:
+                break
+        if not self.history:
             dev.sync()
-            self.history = []
+        self.solver.x.mark_device_modified()
+        self.corrections = applied
         return self.history
 
     def _residual(self, b, x, k: int) -> None:
-        """r = b - A x with consistent shared rows; owned squared norms of r and b -> slot k."""
+        """r = b - A x with consistent shared rows and the global [||r||^2, ||b||^2] in slot k:
+        one all-reduce of n_shared + 2 doubles."""
         dev = self.dev
-        dev.call("nxfx_residual", b, x, self._r.c_ptr, None)
-        if self.part.shared_lm.size:
-            sh = self._ptr(self._sh)
-            dev.call("nxfx_pack_shared", self._r.c_ptr, sh)
-            self._dist.all_reduce(self._sh[: self.part.shared_lm.size], group=self._group)
-            dev.call("nxfx_unpack_shared", sh, self._r.c_ptr)
-        dev.call("nxfx_norm2_owned", self._r.c_ptr, self._ptr(self._nrm, 2 * k))
-        dev.call("nxfx_norm2_owned", b, self._ptr(self._nrm, 2 * k + 1))
+        sh = self._ptr(self._sh)
+        dev.call("nxfx_residual_partial", b, x, self._r.c_ptr, sh)
+        self._dist.all_reduce(self._sh, group=self._group)
+        dev.call("nxfx_residual_finish", sh, self._r.c_ptr, self._ptr(self._nrm, 2 * k))
 
     # ---- results -------------------------------------------------------------------------------
     def local_solution(self) -> np.ndarray:

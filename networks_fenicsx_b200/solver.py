@@ -31,8 +31,8 @@ class Solver:
         petsc_options: Dictionary of PETSc-style options, see :class:`la.KSP`. Extra keys:
             ``nxfx_refine_steps`` (iterative-refinement steps of the direct solve, default 1),
             ``nxfx_final_residual`` (also evaluate the true residual of the final iterate),
-            ``nxfx_refine_rtol`` (default 1e-13: a refinement step is skipped on the device when the
-            iterate already has that relative residual; 0 = always refine).
+            ``nxfx_refine_rtol`` (default 1e-13: refinement stops as soon as the iterate has that relative
+            residual; 0 = always apply ``nxfx_refine_steps`` corrections).
         kind: ``None``/``"mpi"`` (monolithic AIJ) or ``"nest"``.
     """
 
