@@ -295,7 +295,7 @@ def run_gpu(args):
             "solver": "preonly: network-Schur direct solve + 1 iterative-refinement step (residual of the first solve checked)",
             "relative_residual_before_refinement": rel_res, "relative_residual_final": rel_res_final,
             "partition": (f"one {n}-generation tree cut into {world} edge partitions (subtrees); {ds.part.n_top} cut multipliers "
-                          "replicated; per solve: 1 all-reduce (setup) + 2 (preconditioner) + 1 (shared rows of A x) + 1 (norms), "
+                          "replicated; per solve: 1 all-reduce (factorisation + first application) + 1 (halo rows of A x + norms), "
                           "torch.distributed/NCCL") if world > 1 else "single GPU",
             "l2": "per-step working set ~0.6 GB > 126 MB L2, no flush",
         },

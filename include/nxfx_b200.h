@@ -214,7 +214,9 @@ int nxfx_assemble_generic(nxfx_ctx* ctx, const double* R_cell_d, double R_const,
  *   buf_d                    caller-owned device buffer, 2*n_top doubles (nxfx_top_size)
  *   nxfx_pc_setup_begin  -> buf = [partial pivots | link conductances] of the top chunk
  *   nxfx_pc_setup_end    <- all-reduced buf: factorises the top chunk (identically on all ranks)
- *   nxfx_pc_apply_begin  -> buf[0:n_top] = partial right-hand side of the top chunk
+ *   nxfx_pc_apply_begin  -> buf[0:n_top] = partial right-hand side of the top chunk (may be called
+ *                        right after nxfx_pc_setup_begin with a second buffer: setup and first
+ *                        application then share ONE all-reduce, followed by _setup_end, _apply_end)
  *   nxfx_pc_apply_end    <- all-reduced buf: top solve, back-substitution; z = or += P^{-1} r
  *   nxfx_pack_shared / nxfx_unpack_shared  shared multiplier rows of a vector <-> buf (after
  *                        y = A x these rows are partial sums)

@@ -61,6 +61,7 @@ struct nxfx_ctx {
 
   // network
   bool has_network = false, has_pattern = false, has_pbc = false, assembled = false, pc_ready = false;
+  bool bottom_factored = false;  // multi-GPU: nxfx_pc_setup_begin done (bottom chunks factorised)
   int32_t n_nodes = 0, E = 0, gdim = 0, N = 0, n_bif = 0, n_inc = 0;
   int64_t nv = 0, nc = 0, nq = 0, poff = 0, loff = 0, ndofs = 0, nnz = 0;
   nxfx::DevBuf<double> x;          // [nv][4] vertex records {x, y, z, p_bc} (graph nodes first)

@@ -720,7 +720,7 @@ int nxfx_assemble(nxfx_ctx* ctx, const double* R_cell, double R_const, const dou
     if (n1) NXFX_LAUNCH(ctx, (assemble_tiles_kernel<false, true>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs, nft, npt);
     else NXFX_LAUNCH(ctx, (assemble_tiles_kernel<false, false>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs, nft, npt);
   }
-  if (lhs) { ctx->assembled = true; ctx->pc_ready = false; }
+  if (lhs) { ctx->assembled = true; ctx->pc_ready = false; ctx->bottom_factored = false; }
   return NXFX_OK;
 }
 
@@ -1007,6 +1007,7 @@ int nxfx_pc_setup_begin(nxfx_ctx* ctx, double* buf) {
   }
   if (nb > 0) NXFX_LAUNCH(ctx, tree_factor_kernel, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
   NXFX_LAUNCH(ctx, (tree_top_kernel<true, kPartial>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
+  ctx->bottom_factored = true;
   return NXFX_OK;
 }
 
@@ -1023,7 +1024,9 @@ int nxfx_pc_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
   if (!ctx || !r) return NXFX_ERR_INVALID;
   int rc = dist_ready(ctx, buf);
   if (rc) return rc;
-  NXFX_REQUIRE(ctx, ctx->pc_ready, "pc_setup has not been run");
+  // the forward sweep of the bottom chunks only needs THEIR factors: it may run before
+  // nxfx_pc_setup_end, so that setup and first application share one all-reduce
+  NXFX_REQUIRE(ctx, ctx->pc_ready || ctx->bottom_factored, "nxfx_pc_setup_begin has not been run");
   Net g = make_net(ctx);
   TreeDev t = make_tree(ctx);
   const int nb = ctx->tree.n_chunks - 1;

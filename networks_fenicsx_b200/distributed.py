@@ -153,7 +153,7 @@ class DistributedSolver:
         weight = np.ascontiguousarray(part.lam_weight, dtype=np.float64)
         self.dev.call("nxfx_set_shared", shared.size, _lib.as_i32p(shared), _lib.as_f64p(weight))
         cuda = torch.device("cuda", device)
-        self._top = torch.zeros(2 * max(part.n_top, 1), dtype=torch.float64, device=cuda)
+        self._top = torch.zeros(3 * max(part.n_top, 1), dtype=torch.float64, device=cuda)  # [setup 2n | apply n]
         self._sh = torch.zeros(shared.size + 2, dtype=torch.float64, device=cuda)  # halo rows + 2 norm partials
         self._nrm = torch.zeros(2 * 40, dtype=torch.float64, device=cuda)
         self._r = self.dev.empty(self.assembler.num_dofs)
@@ -185,16 +185,20 @@ class DistributedSolver:
         """x = P^{-1} b, then iterative refinement while ``||b - A x|| > refine_rtol ||b||`` (at most
         ``refine_steps`` corrections; the all-reduced norms are identical on every rank, so all
         ranks take the same decision).  Returns the global relative residual norms that were
-        evaluated.  Collectives: 1 (setup) + 1 per preconditioner application + 1 per residual
-        (halo rows and norm partials travel in one buffer)."""
+        evaluated.  Collectives: 1 (setup fused with the first application) + 1 per residual (halo rows
+        and norm partials in one buffer) + 1 per correction."""
         dev = self.dev
         b = self.solver.b.device_ptr()
         x = self.solver.x.device_ptr_overwrite()
-        top = self._ptr(self._top)
+        # factorisation and first application share one all-reduce: the forward sweep of the bottom
+        # chunks only needs their own factors
+        nt = max(self.part.n_top, 1)
+        top, top_rhs = self._ptr(self._top), self._ptr(self._top, 2 * nt)
         dev.call("nxfx_pc_setup_begin", top)
+        dev.call("nxfx_pc_apply_begin", b, top_rhs)
         self._dist.all_reduce(self._top, group=self._group)
         dev.call("nxfx_pc_setup_end", top)
-        self._apply(b, x, 0)
+        dev.call("nxfx_pc_apply_end", b, x, top_rhs, 0)
         self.history = []
         applied = 0
         while refine_steps > 0 or final_residual:
