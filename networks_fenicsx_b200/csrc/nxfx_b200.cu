@@ -192,20 +192,26 @@ int do_multi_axpy(nxfx_ctx* ctx, int n, int k, const double* A, size_t stride, c
 
 int ensure_work(nxfx_ctx* ctx, size_t nvec);
 
-int tree_pass(nxfx_ctx* ctx, bool factor) {
+// fused: N == 1 -- the kernels evaluate the nodes' diagonal / right-hand side themselves from
+// (r, cell_rh); returns through *did_fuse whether the separate bif_* kernel is still needed.
+int tree_pass(nxfx_ctx* ctx, bool factor, const double* fuse_r = nullptr, bool fuse = false, bool* did_fuse = nullptr) {
   auto& s = ctx->tree;
   TreeDev t = make_tree(ctx);
   const int nb = s.n_chunks - 1;  // bottom chunks; the last chunk is the top of the forest
   if (s.fast_ok) {
     const int grid = std::max(nb, 1);
     unsigned int* tk = ctx->ticket.p + 1;
+    FusedN1 fin{make_net(ctx), nullptr, nullptr};
+    if (did_fuse) *did_fuse = false;
     if (factor) {
-      NXFX_LAUNCH(ctx, tree_factor_kernel, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1);
+      if (fuse) { fin.cell_rh = ctx->cell_rh.p; if (did_fuse) *did_fuse = true; }
+      NXFX_LAUNCH(ctx, tree_factor_kernel, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1, fin);
     } else if (s.coop_ok && nb > 0) {
+      if (fuse) { fin.r = fuse_r; fin.cell_rh = ctx->cell_rh.p; if (did_fuse) *did_fuse = true; }
       unsigned int* fl = ctx->ticket.p + 2;
       unsigned int ep = ++s.epoch;
       int nbv = nb;
-      void* args[] = {&t, &nbv, &tk, &fl, &ep};
+      void* args[] = {&t, &nbv, &tk, &fl, &ep, &fin};
       NXFX_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tree_solve_coop_kernel), dim3(nb), dim3(kTreeThreads),
                                                  args, sizeof(TreeSmem), ctx->stream));
       ctx->launches++;
@@ -234,13 +240,11 @@ int do_pc_setup(nxfx_ctx* ctx) {
     NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N,
                 ctx->cell_rh.p, ctx->edge_g.p);
   if (ctx->n_bif > 0) {
-    if (n1)
-      NXFX_LAUNCH(ctx, bif_diag_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx),
-                  make_tree(ctx), ctx->cell_rh.p);
-    else
+    if (!n1) {
       NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx),
                   make_tree(ctx), ctx->edge_g.p);
-    int rc = tree_pass(ctx, true);
+    }
+    int rc = tree_pass(ctx, true, nullptr, n1);  // N == 1: the factor kernel evaluates the diagonals itself
     if (rc) return rc;
   }
   ctx->pc_ready = true;
@@ -272,9 +276,12 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
   const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
   if (ctx->N == 1 && ctx->tree.fast_ok) {
     if (ctx->n_bif > 0) {
-      NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cell_rh.p,
-                  ctx->lam_weight.p);
-      int rc = tree_pass(ctx, false);
+      // single-launch solve: the tree kernel evaluates the bifurcation right-hand sides itself
+      const bool fuse = ctx->tree.coop_ok && ctx->tree.n_chunks > 1 && !ctx->lam_weight.p;
+      if (!fuse)
+        NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cell_rh.p,
+                    ctx->lam_weight.p);
+      int rc = tree_pass(ctx, false, r, fuse);
       if (rc) return rc;
     }
     if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
@@ -1005,7 +1012,8 @@ int nxfx_pc_setup_begin(nxfx_ctx* ctx, double* buf) {
     NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N, ctx->cell_rh.p, ctx->edge_g.p);
     NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx), t, ctx->edge_g.p);
   }
-  if (nb > 0) NXFX_LAUNCH(ctx, tree_factor_kernel, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_factor_kernel, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0,
+                          (FusedN1{make_net(ctx), nullptr, nullptr}));
   NXFX_LAUNCH(ctx, (tree_top_kernel<true, kPartial>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
   ctx->bottom_factored = true;
   return NXFX_OK;

@@ -40,6 +40,35 @@ struct TreeDev {
   double* lam_nat;  // natural (bifurcation) order, read by the back-substitution
 };
 
+// N == 1 fusion: the tree kernels can evaluate a node's Laplacian diagonal / right-hand side on the
+// fly from (r, cell_rh) while they stage a chunk, instead of reading arrays that a separate kernel
+// filled (one launch and one 8-byte-per-node round trip less).  r == nullptr: not fused.
+struct FusedN1 {
+  Net g;
+  const double* r;
+  const double* cell_rh;
+};
+
+__device__ __forceinline__ double n1_bif_rhs(const FusedN1& f, int bi) {
+  const Net& g = f.g;
+  double s = -f.r[g.loff + bi];
+  for (int k = g.bif_ptr[bi]; k < g.bif_ptr[bi + 1]; ++k) {
+    const int inc = g.bif_inc[k], e = inc >> 1;
+    const double2 rq = *reinterpret_cast<const double2*>(f.r + 2 * (size_t)g.edge_slot[e]);
+    const double rp = f.r[g.poff + e], rh = f.cell_rh[e];
+    const double gc = ((rq.x + rq.y) - 0.5 * rh * rp) / rh;
+    s += (inc & 1) ? (rp + gc) : -gc;
+  }
+  return s;
+}
+
+__device__ __forceinline__ double n1_bif_diag(const FusedN1& f, int bi) {
+  const Net& g = f.g;
+  double s = 0.0;
+  for (int k = g.bif_ptr[bi]; k < g.bif_ptr[bi + 1]; ++k) s += 1.0 / f.cell_rh[g.bif_inc[k] >> 1];
+  return s;
+}
+
 // g_e = 1 / sum_j R_j h_j
 __global__ void __launch_bounds__(kThreads)
 edge_conductance_kernel(int E, int N, const double* __restrict__ cell_rh, double* __restrict__ g) {
@@ -205,12 +234,21 @@ enum { kFull = 0, kPartial = 1, kFinish = 2 };
 // t.d receives 1/d.  `top`: children below b0 live in bottom chunks (already written to HBM).
 // buf (top chunk, kPartial/kFinish): [partial d | tg], 2*nn doubles.
 __device__ __forceinline__ void factor_chunk(const TreeDev& t, TreeSmem& S, int chunk, bool top,
-                                             int phase = kFull, double* buf = nullptr) {
+                                             int phase = kFull, double* buf = nullptr,
+                                             const FusedN1* f = nullptr) {
   const ChunkInfo ci = load_chunk_info(t, chunk, S);
   const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
   load_children(t, ci, S);
   if (phase == kFinish) {
     for (int i = tid; i < nn; i += nth) { S.a[i] = buf[i]; S.b[i] = buf[nn + i]; }
+  } else if (f) {
+    for (int i = tid; i < nn; i += nth) {
+      S.a[i] = n1_bif_diag(*f, t.bif_of_t[b0 + i]);
+      const int pe = t.t_pedge[b0 + i];
+      const double tg = pe >= 0 ? 1.0 / f->cell_rh[pe] : 0.0;
+      S.b[i] = tg;
+      t.tg[b0 + i] = tg;  // the top chunk reads the link conductances of its bottom-chunk children
+    }
   } else {
     for (int i = tid; i < nn; i += nth) { S.a[i] = t.diag0[b0 + i]; S.b[i] = t.tg[b0 + i]; }
   }
@@ -247,10 +285,11 @@ __device__ __forceinline__ void factor_chunk(const TreeDev& t, TreeSmem& S, int 
 }
 
 // stage a chunk for the solve: a = r, b = 1/d, c = gd, par
-__device__ __forceinline__ void load_solve_chunk(const TreeDev& t, const ChunkInfo& ci, TreeSmem& S) {
+__device__ __forceinline__ void load_solve_chunk(const TreeDev& t, const ChunkInfo& ci, TreeSmem& S,
+                                                 const FusedN1* f = nullptr) {
   const int nn = ci.b1 - ci.b0;
   for (int i = threadIdx.x; i < nn; i += blockDim.x) {
-    S.a[i] = t.r[ci.b0 + i];
+    S.a[i] = f ? n1_bif_rhs(*f, t.bif_of_t[ci.b0 + i]) : t.r[ci.b0 + i];
     S.b[i] = t.d[ci.b0 + i];
     S.c[i] = t.gd[ci.b0 + i];
     S.par[i] = t.t_parent[ci.b0 + i];
@@ -319,16 +358,17 @@ __device__ __forceinline__ bool last_block_done(TreeSmem& S, unsigned int* ticke
 
 // grid = max(n_bottom, 1); do_top = 0 (multi-GPU): bottom chunks only
 __global__ void __launch_bounds__(kTreeThreads)
-tree_factor_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top) {
+tree_factor_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top, FusedN1 fin) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
   TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
+  const FusedN1* f = fin.cell_rh ? &fin : nullptr;
   if (n_bottom > 0) {
-    factor_chunk(t, S, blockIdx.x, false);
+    factor_chunk(t, S, blockIdx.x, false, kFull, nullptr, f);
     if (!do_top) return;
     if (!last_block_done(S, ticket, n_bottom)) return;
   }
   if (!do_top) return;
-  factor_chunk(t, S, n_bottom, true);
+  factor_chunk(t, S, n_bottom, true, kFull, nullptr, f);
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
@@ -388,12 +428,14 @@ tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top) {
 
 // single-launch solve: requires all n_bottom blocks to be co-resident (cooperative launch)
 __global__ void __launch_bounds__(kTreeThreads)
-tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch) {
+tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch,
+                       FusedN1 fin) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
   TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
+  const FusedN1* f = fin.r ? &fin : nullptr;
   const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
   load_children(t, ci, S);
-  load_solve_chunk(t, ci, S);
+  load_solve_chunk(t, ci, S, f);
   __syncthreads();
   solve_up(t, S, ci, false);
   // publish the chunk roots (the shallowest levels may hold several subtree roots: publish the
@@ -406,7 +448,7 @@ tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned i
     __syncthreads();
     const ChunkInfo ti = load_chunk_info(t, n_bottom, S);
     load_children(t, ti, S);
-    load_solve_chunk(t, ti, S);
+    load_solve_chunk(t, ti, S, f);
     __syncthreads();
     solve_up(t, S, ti, true);
     solve_down(t, S, ti);
