@@ -84,8 +84,11 @@ def spanning_forest(edges: np.ndarray, node_lm: np.ndarray, n_bif: int,
         hint = np.zeros(node_lm.size, dtype=bool)
         hint[root_hint_nodes] = True
         roots = np.unique(np.concatenate([b[hint[u] & (b >= 0)], a[hint[v] & (a >= 0)]])).astype(np.int64)
-        if roots.size:
-            bfs(roots, 0)
+        # one root per connected component: a component with several inlets must not be grown from
+        # several roots at once (the edge where two fronts meet would be mistaken for a chord)
+        while roots.size:
+            bfs(roots[:1], 0)
+            roots = roots[depth[roots] < 0]
     while True:
         rest = np.flatnonzero(depth < 0)
         if rest.size == 0:

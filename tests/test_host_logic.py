@@ -352,3 +352,16 @@ def test_higher_order_known_answers():
     x_ho = ho.solve(*ho.assemble(pbc, R=1.7))
     np.testing.assert_allclose(x_ho[ho.fb], x_lo[lo.fb], rtol=1e-10, atol=1e-13)
     np.testing.assert_allclose(x_ho[ho.loff:], x_lo[lo.loff:], rtol=1e-10, atol=1e-13)
+
+
+def test_schedule_of_tree_with_many_inlets_is_a_forest():
+    """Regression (found by the property tests): a component with several inlets must be grown
+    from ONE root, otherwise the edge where two BFS fronts meet is mistaken for a cycle."""
+    A = ng.make_tree(7, 1, 1, as_arrays=True)
+    rev = ng.ArrayGraph(A.pos, A.edges[:, ::-1].copy())  # every leaf becomes an inlet
+    nm = nxfx.NetworkMesh(rev, N=2)
+    assert nm._boundary_out_nodes.size == 64
+    s = build_tree_schedule(nm.graph_edges, nm.node_multiplier_index, nm.bifurcation_values.size,
+                            root_hint_nodes=nm._boundary_out_nodes, chunk_nodes=16)
+    assert s.is_forest
+    check_schedule(nm, s, 16)
