@@ -190,6 +190,7 @@ int do_multi_axpy(nxfx_ctx* ctx, int n, int k, const double* A, size_t stride, c
   return NXFX_OK;
 }
 
+inline size_t vec_stride(const nxfx_ctx* ctx);
 int ensure_work(nxfx_ctx* ctx, size_t nvec);
 
 // fused: N == 1 -- the kernels evaluate the nodes' diagonal / right-hand side themselves from
@@ -256,7 +257,7 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
   if (add && pc_type != NXFX_PC_NETWORK_SCHUR) {  // generic: z_tmp = P^{-1} r, z += z_tmp
     int rc = ensure_work(ctx, 3);
     if (rc) return rc;
-    double* tmp = ctx->work.p + 2 * (size_t)n;
+    double* tmp = ctx->work.p + 2 * vec_stride(ctx);
     if ((rc = do_pc_apply(ctx, pc_type, r, tmp, false))) return rc;
     NXFX_LAUNCH(ctx, add_kernel, vec_grid(ctx, n), kThreads, 0, n, tmp, z);
     return NXFX_OK;
@@ -275,6 +276,9 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
   TreeDev t = make_tree(ctx);
   const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
   if (ctx->N == 1 && ctx->tree.fast_ok) {
+    // the N == 1 kernels move the two flux dofs of an edge with one 16-byte access
+    NXFX_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(r) & 15) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0,
+                 "vectors must be 16-byte aligned");
     if (ctx->n_bif > 0) {
       // single-launch solve: the tree kernel evaluates the bifurcation right-hand sides itself
       const bool fuse = ctx->tree.coop_ok && ctx->tree.n_chunks > 1 && !ctx->lam_weight.p;
@@ -303,8 +307,12 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
   return NXFX_OK;
 }
 
+// Krylov / work vectors are laid out with an EVEN stride: the N == 1 kernels read pairs of flux
+// dofs with 16-byte loads, so every vector must start on a 16-byte boundary.
+inline size_t vec_stride(const nxfx_ctx* ctx) { return ((size_t)ctx->ndofs + 1) & ~(size_t)1; }
+
 int ensure_work(nxfx_ctx* ctx, size_t nvec) {
-  const size_t need = nvec * (size_t)ctx->ndofs;
+  const size_t need = nvec * vec_stride(ctx);
   if (ctx->work.n >= need) return NXFX_OK;
   NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   NXFX_CUDA(ctx, ctx->work.alloc(need));
@@ -363,10 +371,11 @@ int solve_fgmres(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opt
   NXFX_REQUIRE(ctx, 2 * (m + 2) + 8 < kScalSlots, "restart too large");
   int rc = ensure_work(ctx, (size_t)(2 * m + 3));
   if (rc) return rc;
+  const size_t ld = vec_stride(ctx);             // even: every vector is 16-byte aligned
   double* V = ctx->work.p;                       // m+1 vectors
-  double* Z = V + (size_t)(m + 1) * n;           // m vectors
-  double* w = Z + (size_t)m * n;                 // 1
-  double* r = w + n;                             // 1
+  double* Z = V + (size_t)(m + 1) * ld;          // m vectors
+  double* w = Z + (size_t)m * ld;                // 1
+  double* r = w + ld;                            // 1
   double* hcol = slot(ctx, 8);                   // h[0..k], then ||w||^2
   double* hcol2 = slot(ctx, 8 + m + 2);          // second Gram-Schmidt pass
   double* ycoef = slot(ctx, 8 + 2 * (m + 2));    // solution of the small system (<= m)
@@ -391,17 +400,17 @@ int solve_fgmres(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opt
     gvec[0] = beta;
     int k = 0;
     for (; k < m && its < max_it; ++k, ++its) {
-      double* vk = V + (size_t)k * n;
-      double* zk = Z + (size_t)k * n;
+      double* vk = V + (size_t)k * ld;
+      double* zk = Z + (size_t)k * ld;
       if ((rc = do_pc_apply(ctx, o->pc_type, vk, zk))) return rc;
       if ((rc = do_spmv(ctx, zk, w))) return rc;
-      if ((rc = do_multi_dot(ctx, n, k + 1, V, n, w, hcol))) return rc;
-      if ((rc = do_multi_axpy(ctx, n, k + 1, V, n, hcol, -1.0, w))) return rc;
-      if ((rc = do_multi_dot(ctx, n, k + 1, V, n, w, hcol2))) return rc;
-      if ((rc = do_multi_axpy(ctx, n, k + 1, V, n, hcol2, -1.0, w))) return rc;
+      if ((rc = do_multi_dot(ctx, n, k + 1, V, ld, w, hcol))) return rc;
+      if ((rc = do_multi_axpy(ctx, n, k + 1, V, ld, hcol, -1.0, w))) return rc;
+      if ((rc = do_multi_dot(ctx, n, k + 1, V, ld, w, hcol2))) return rc;
+      if ((rc = do_multi_axpy(ctx, n, k + 1, V, ld, hcol2, -1.0, w))) return rc;
       if ((rc = do_multi_dot(ctx, n, 1, w, 0, w, hcol + k + 1))) return rc;
       NXFX_LAUNCH(ctx, scale_by_inv_norm_kernel, vec_grid(ctx, n), kThreads, 0, n, w, hcol + k + 1,
-                  V + (size_t)(k + 1) * n);
+                  V + (size_t)(k + 1) * ld);
       NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, hcol, (2 * (m + 2)) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
       NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       double* Hk = &H[(size_t)k * (m + 1)];
@@ -430,7 +439,7 @@ int solve_fgmres(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opt
     if (k > 0) {
       std::copy(y.begin(), y.begin() + k, ctx->scal_h + 512);
       NXFX_CUDA(ctx, cudaMemcpyAsync(ycoef, ctx->scal_h + 512, k * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-      if ((rc = do_multi_axpy(ctx, n, k, Z, n, ycoef, 1.0, x))) return rc;
+      if ((rc = do_multi_axpy(ctx, n, k, Z, ld, ycoef, 1.0, x))) return rc;
     }
   }
   info->iterations = its;
@@ -710,6 +719,7 @@ int nxfx_assemble(nxfx_ctx* ctx, const double* R_cell, double R_const, const dou
   NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
   NXFX_REQUIRE(ctx, !ctx->generic, "higher-order pattern loaded: use nxfx_assemble_generic");
   NXFX_REQUIRE(ctx, !rhs || (b && ctx->has_pbc), "rhs requested without b / boundary pressure");
+  NXFX_REQUIRE(ctx, !rhs || (reinterpret_cast<uintptr_t>(b) & 15) == 0, "b must be 16-byte aligned");
   if (!lhs && !rhs) return NXFX_OK;
   Net g = make_net(ctx);
   Coef c;
@@ -1035,6 +1045,7 @@ int nxfx_pc_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
   // the forward sweep of the bottom chunks only needs THEIR factors: it may run before
   // nxfx_pc_setup_end, so that setup and first application share one all-reduce
   NXFX_REQUIRE(ctx, ctx->pc_ready || ctx->bottom_factored, "nxfx_pc_setup_begin has not been run");
+  NXFX_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(r) & 15) == 0, "vectors must be 16-byte aligned");
   Net g = make_net(ctx);
   TreeDev t = make_tree(ctx);
   const int nb = ctx->tree.n_chunks - 1;

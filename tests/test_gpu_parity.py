@@ -395,3 +395,42 @@ def test_adaptive_refinement():
         assert solver.info.residual_norm <= 1e-10 * solver.info.rhs_norm
     assert its["forced"] == 2 and its["tight"] == 2 and its["none"] == 1 and its["default"] in (1, 2)
     assert helpers.rel_l2(xs["forced"], xs["tight"]) == 0.0
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_graphs_with_random_orientation(seed):
+    """Random recursive trees with random edge directions (several inlets / outlets per component)
+    plus, for odd seeds, a few cycle-closing edges: pattern, values and solution against the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(5, 60))
+    G = nx.DiGraph()
+    for i in range(n):
+        G.add_node(i, pos=rng.normal(size=3))
+    und = set()
+    for k in range(1, n):
+        p = 0 if k == 1 else int(rng.integers(0, k))
+        und.add((p, k))
+        G.add_edge(*((p, k) if rng.random() < 0.5 else (k, p)))
+    if seed % 2:
+        for _ in range(3):
+            a, b = (int(v) for v in rng.integers(0, n, 2))
+            if a != b and (min(a, b), max(a, b)) not in und:
+                und.add((min(a, b), max(a, b)))
+                G.add_edge(a, b)
+    N = int(rng.integers(1, 5))
+    nc = N * G.number_of_edges()
+    nm, asm, solver, sol, net, A, b = run_case(G, N, "largest_first" if seed % 3 else None,
+                                               lambda x: x[0] - x[1] + 0.3 * x[2],
+                                               R=rng.uniform(0.5, 2.0, nc), f=rng.normal(size=nc))
+    check_system(solver, net, A, b)
+    check_solution(sol, net, A, b, tol=1e-9)
+    assert solver._schedule.is_forest == (A.shape[0] > 0 and nx.is_forest(G.to_undirected()))
+
+
+def test_reversed_tree_many_inlets():
+    A_ = ng.make_tree(9, 2, 3, as_arrays=True)
+    rev = ng.ArrayGraph(A_.pos, A_.edges[:, ::-1].copy())
+    nm, asm, solver, sol, net, A, b = run_case(rev, 2, "smallest_last", P_Y)
+    assert solver._schedule.is_forest
+    check_system(solver, net, A, b)
+    check_solution(sol, net, A, b)
