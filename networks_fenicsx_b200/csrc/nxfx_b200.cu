@@ -782,7 +782,9 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
   s.fast_ok = true;
   for (int c = 0; c < n_chunks; ++c) {
     const int l0 = chunk_lptr[c], l1 = chunk_lptr[c + 1];
-    if (l1 - l0 > kLevelCap || lvl_ptr[l1] - lvl_ptr[l0] > kChunkCap) s.fast_ok = false;
+    if (l1 - l0 > kLevelCap || lvl_ptr[l1] - lvl_ptr[l0] > kChunkCap ||
+        t_cptr[lvl_ptr[l1]] - t_cptr[lvl_ptr[l0]] > kChildCap)
+      s.fast_ok = false;
   }
   if (s.fast_ok) {
     std::vector<int32_t> desc((size_t)n_chunks * kDescInts, 0);

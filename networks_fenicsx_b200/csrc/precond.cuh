@@ -155,6 +155,7 @@ tree_sweep_kernel(TreeDev t, const double* __restrict__ edge_g, int chunk0) {
 // application.  Trees with more chunks than resident blocks use two launches (up, down).
 constexpr int kChunkCap = 2048;  // nodes per chunk held in shared memory
 constexpr int kLevelCap = 64;    // levels per chunk held in shared memory
+constexpr int kChildCap = 4096;  // child links per chunk (the top chunk also lists its bottom-chunk children)
 constexpr int kDescInts = 8 + kLevelCap + 1;  // {b0, b1, cb, ce, nl, Lw, -, -, lvl[0..nl]}
 #ifndef NXFX_TREE_THREADS
 #define NXFX_TREE_THREADS 1024
@@ -166,7 +167,7 @@ struct TreeSmem {
   double b[kChunkCap];  // F: tg         solve: 1/d
   double c[kChunkCap];  // F: gd         solve: gd
   int cptr[kChunkCap + 1];
-  int cidx[kChunkCap];
+  int cidx[kChildCap];
   int par[kChunkCap];
   int lvl[kLevelCap + 1];
   int last;

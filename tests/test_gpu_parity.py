@@ -434,3 +434,28 @@ def test_reversed_tree_many_inlets():
     assert solver._schedule.is_forest
     check_system(solver, net, A, b)
     check_solution(sol, net, A, b)
+
+
+def test_top_chunk_with_many_child_links():
+    """Regression: the top chunk lists its own links AND the roots of all bottom chunks; with tiny
+    bottom chunks that is about twice its node count (here 2047 nodes, 4094 links), which used to
+    overflow the shared-memory child table (first seen on a 23-generation tree)."""
+    from networks_fenicsx_b200.schedule import build_tree_schedule
+
+    G = ng.make_tree(14, 3, 5, as_arrays=True)
+    nm = nxfx.NetworkMesh(G, N=1, color_strategy="smallest_last")
+    asm = nxfx.HydraulicNetworkAssembler(nm)
+    asm.compute_forms(p_bc_ex=P_Y)
+    sched = build_tree_schedule(nm.graph_edges, nm.node_multiplier_index, nm.bifurcation_values.size,
+                                root_hint_nodes=nm._boundary_out_nodes, chunk_nodes=4)
+    top = sched.lvl_ptr[sched.chunk_lptr[-1]] - sched.lvl_ptr[sched.chunk_lptr[-2]]
+    links = sched.t_cptr[sched.lvl_ptr[sched.chunk_lptr[-1]]] - sched.t_cptr[sched.lvl_ptr[sched.chunk_lptr[-2]]]
+    assert top == 2047 and links == 4094
+    solver = nxfx.Solver(asm, schedule=sched, petsc_options={"ksp_type": "preonly", "pc_type": "lu",
+                                                             "nxfx_final_residual": True, "nxfx_refine_steps": 0})
+    solver.assemble()
+    sol = solver.solve()
+    net = helpers.oracle_for(nm, 1)
+    A, b = net.assemble(net.eval_pbc(P_Y))
+    check_solution(sol, net, A, b)
+    assert solver.info.residual_norm <= 1e-12 * solver.info.rhs_norm
