@@ -294,6 +294,7 @@ def run_gpu(args):
             "graph_edges_per_gpu": E,
             "solver": "preonly: network-Schur direct solve + 1 iterative-refinement step (residual of the first solve checked)",
             "relative_residual_before_refinement": rel_res, "relative_residual_final": rel_res_final,
+            "refinement_corrections_per_step": int(ds.corrections) if ds is not None else int(info.iterations) - 1,
             "partition": (f"one {n}-generation tree cut into {world} edge partitions (subtrees); {ds.part.n_top} cut multipliers "
                           "replicated; per solve: 1 all-reduce (factorisation + first application) + 1 (halo rows of A x + norms), "
                           "torch.distributed/NCCL") if world > 1 else "single GPU",

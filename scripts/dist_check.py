@@ -30,6 +30,7 @@ def main():
     ds = DistributedSolver(G, N, p_bc, device=local_rank, chunk_nodes=chunk)
     ds.assemble()
     hist = ds.solve(refine_steps=1, final_residual=True)
+    assert ds.corrections == 0, f"the distributed direct solve needed {ds.corrections} correction(s) on a tree: {hist}"
     ge, q, p, gl, lam = ds.edge_values()
     gathered = [None] * world
     dist.gather_object((ge, q, p, gl, lam), gathered if rank == 0 else None, dst=0)

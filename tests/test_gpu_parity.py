@@ -101,6 +101,9 @@ def test_tree(n, N):
     nm, asm, solver, sol, net, A, b = run_case(G, N, "smallest_last", P_Y)
     check_system(solver, net, A, b)
     x, x_ref = check_solution(sol, net, A, b)
+    # on a tree the Schur preconditioner is an exact solve: no refinement correction may be needed
+    # (a correction being applied here means the preconditioner is broken and merely being repaired)
+    assert solver.ksp.getIterationNumber() == 1 and solver.info.residual_norm <= 1e-13 * solver.info.rhs_norm
     # closed form: resistor network with boundary pressures -p_bc
     q_edge, lam = net.resistor_network_solution(net.eval_pbc(P_Y))
     np.testing.assert_allclose(sol[-1].x.array, lam, rtol=1e-9, atol=1e-12)
@@ -241,6 +244,7 @@ def test_full_size_properties():
     n_bif = nm.bifurcation_values.size
     assert asm.num_dofs == 3670012 and solver.A.nnz == 14680044 == E * 8 + 4 * (2 * E - nm.boundary_values.size)
     assert solver.info.residual_norm <= 1e-13 * solver.info.rhs_norm
+    assert solver.ksp.getIterationNumber() == 1, "the direct solve needed a refinement correction on a tree"
     rp_, ci, va = solver.A.getValuesCSR()
     A = sp.csr_matrix((va, ci, rp_), shape=(asm.num_dofs,) * 2)
     x = np.concatenate([f.x.array for f in sol])
