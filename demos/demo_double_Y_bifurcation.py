@@ -1,20 +1,23 @@
-"""Wider Y bifurcation with p_bc = x (BASELINE config 1; reference demos/demo_double_Y_bifurcation.py)."""
-from pathlib import Path
+"""Wide Y bifurcation driven by p = x -- BASELINE config 1, the workload of the reference's
+demos/demo_double_Y_bifurcation.py (make_tree(2, 3.1, 7.3), 5 cells per edge).  By symmetry the
+stem carries no flux and the two branches carry +-0.9204."""
+import pathlib
 
-from networks_fenicsx_b200 import HydraulicNetworkAssembler, NetworkMesh, Solver, fem, network_generation
-from networks_fenicsx_b200.post_processing import export_functions, extract_global_flux
+import networks_fenicsx_b200 as nxfx
 
-G = network_generation.make_tree(2, 3.1, 7.3)
-network_mesh = NetworkMesh(G, N=5)
-x = fem.SpatialCoordinate(network_mesh.mesh)
 
-assembler = HydraulicNetworkAssembler(network_mesh)
-assembler.compute_forms(p_bc_ex=x[0])
+def main() -> list:
+    net = nxfx.NetworkMesh(nxfx.network_generation.make_tree(2, 3.1, 7.3), N=5)
+    problem = nxfx.HydraulicNetworkAssembler(net)
+    problem.compute_forms(p_bc_ex=nxfx.fem.SpatialCoordinate(net.mesh)[0])
+    ksp = nxfx.Solver(problem)
+    ksp.assemble()
+    fields = ksp.solve()
+    nxfx.post_processing.export_functions(fields, pathlib.Path(__file__).parent / "results_double_Y_bifurcation")
+    flux = nxfx.post_processing.extract_global_flux(net, fields)
+    print("double Y: fluxes", [float(f.x.array[0]) for f in fields[:-2]], "| global flux dofs:", flux.x.array.size)
+    return fields
 
-solver = Solver(assembler)
-solver.assemble()
-sol = solver.solve()
 
-global_flux = extract_global_flux(network_mesh, sol)
-export_functions(sol, outpath=Path(__file__).parent / "results_double_Y_bifurcation")
-print("double Y: fluxes", [float(f.x.array[0]) for f in sol[:-2]])
+if __name__ == "__main__":
+    main()
