@@ -362,8 +362,10 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1 and args.scaling == "weak":
         n += max(0, (world - 1).bit_length())  # same workload rule as the GPU arm
-    est = 8.0 * 4 ** (n - 20) if n >= 20 else 8.0 / 4 ** (20 - n)
-    n_ref = n
+    # measured: 2.7 s per step at n = 20 (cost and memory grow linearly: x2 per generation); the
+    # sample is bounded by ~150 s of CPU work and by n <= 21 (SuperLU memory at larger sizes)
+    n_ref = min(n, 21)
+    est = 3.0 * 2.0 ** (n_ref - 20)
     while n_ref > 10 and est * (args.steps + args.warmup) > 150.0:
         n_ref -= 1
         est /= 2.0
