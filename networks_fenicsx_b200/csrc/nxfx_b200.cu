@@ -47,6 +47,7 @@ TreeDev make_tree(nxfx_ctx* c) {
   t.bif_of_t = s.bif_of_t.p;
   t.chunk_desc = s.chunk_desc.p;
   t.lam_nat = s.lam_nat.p;
+  t.cap = s.cap;
   t.t_parent = s.t_parent.p;
   t.t_pedge = s.t_pedge.p;
   t.t_cptr = s.t_cptr.p;
@@ -206,7 +207,7 @@ int tree_pass(nxfx_ctx* ctx, bool factor, const double* fuse_r = nullptr, bool f
     if (did_fuse) *did_fuse = false;
     if (factor) {
       if (fuse) { fin.cell_rh = ctx->cell_rh.p; if (did_fuse) *did_fuse = true; }
-      NXFX_LAUNCH(ctx, tree_factor_kernel, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1, fin);
+      NXFX_LAUNCH(ctx, tree_factor_kernel, grid, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, tk, 1, fin);
     } else if (s.coop_ok && nb > 0) {
       if (fuse) { fin.r = fuse_r; fin.cell_rh = ctx->cell_rh.p; if (did_fuse) *did_fuse = true; }
       unsigned int* fl = ctx->ticket.p + 2;
@@ -214,11 +215,11 @@ int tree_pass(nxfx_ctx* ctx, bool factor, const double* fuse_r = nullptr, bool f
       int nbv = nb;
       void* args[] = {&t, &nbv, &tk, &fl, &ep, &fin};
       NXFX_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tree_solve_coop_kernel), dim3(nb), dim3(kTreeThreads),
-                                                 args, sizeof(TreeSmem), ctx->stream));
+                                                 args, tree_smem_bytes(ctx->tree.cap), ctx->stream));
       ctx->launches++;
     } else {
-      NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, grid, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1);
-      if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, tk, 1);
+      NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, grid, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, tk, 1);
+      if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, tk, 1);
     }
     return NXFX_OK;
   }
@@ -780,12 +781,15 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
   s.n_top = lvl_ptr[chunk_lptr[n_chunks]] - lvl_ptr[chunk_lptr[n_chunks - 1]];
   // shared-memory sweeps need every chunk (nodes, levels) to fit the on-chip tables
   s.fast_ok = true;
+  int max_nodes = 0, max_links = 0;
   for (int c = 0; c < n_chunks; ++c) {
     const int l0 = chunk_lptr[c], l1 = chunk_lptr[c + 1];
-    if (l1 - l0 > kLevelCap || lvl_ptr[l1] - lvl_ptr[l0] > kChunkCap ||
-        t_cptr[lvl_ptr[l1]] - t_cptr[lvl_ptr[l0]] > kChildCap)
-      s.fast_ok = false;
+    if (l1 - l0 > kLevelCap) s.fast_ok = false;
+    max_nodes = std::max(max_nodes, lvl_ptr[l1] - lvl_ptr[l0]);
+    max_links = std::max(max_links, t_cptr[lvl_ptr[l1]] - t_cptr[lvl_ptr[l0]]);
   }
+  s.cap = (max_nodes <= 2048 && max_links <= 4096) ? 2048 : kChunkCapMax;
+  if (max_nodes > s.cap || max_links > 2 * s.cap) s.fast_ok = false;
   if (s.fast_ok) {
     std::vector<int32_t> desc((size_t)n_chunks * kDescInts, 0);
     for (int c = 0; c < n_chunks; ++c) {
@@ -804,17 +808,17 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
     int coop = 0, per_sm = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
     if (coop && cudaFuncSetAttribute(tree_solve_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(TreeSmem)) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_solve_coop_kernel, kTreeThreads, sizeof(TreeSmem)) == cudaSuccess)
+                                     (int)tree_smem_bytes(kChunkCapMax)) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_solve_coop_kernel, kTreeThreads, tree_smem_bytes(ctx->tree.cap)) == cudaSuccess)
       s.coop_ok = (n_chunks - 1) <= per_sm * ctx->sm_count;
     cudaGetLastError();
-    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
-    NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<true, kPartial>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
-    NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<true, kFinish>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
-    NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<false, kPartial>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
-    NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<false, kFinish>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
-    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_solve_kernel<kTreeUp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
-    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_solve_kernel<kTreeDown>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeSmem)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<true, kPartial>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<true, kFinish>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<false, kPartial>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<false, kFinish>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_solve_kernel<kTreeUp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_solve_kernel<kTreeDown>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));
   }
   NXFX_CUDA(ctx, s.tg.alloc(nb));
   NXFX_CUDA(ctx, s.diag0.alloc(nb));
@@ -1024,9 +1028,9 @@ int nxfx_pc_setup_begin(nxfx_ctx* ctx, double* buf) {
     NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N, ctx->cell_rh.p, ctx->edge_g.p);
     NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx), t, ctx->edge_g.p);
   }
-  if (nb > 0) NXFX_LAUNCH(ctx, tree_factor_kernel, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0,
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_factor_kernel, nb, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, ctx->ticket.p + 1, 0,
                           (FusedN1{make_net(ctx), nullptr, nullptr}));
-  NXFX_LAUNCH(ctx, (tree_top_kernel<true, kPartial>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
+  NXFX_LAUNCH(ctx, (tree_top_kernel<true, kPartial>), 1, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, buf);
   ctx->bottom_factored = true;
   return NXFX_OK;
 }
@@ -1035,7 +1039,7 @@ int nxfx_pc_setup_end(nxfx_ctx* ctx, double* buf) {
   if (!ctx) return NXFX_ERR_INVALID;
   int rc = dist_ready(ctx, buf);
   if (rc) return rc;
-  NXFX_LAUNCH(ctx, (tree_top_kernel<true, kFinish>), 1, kTreeThreads, sizeof(TreeSmem), make_tree(ctx), ctx->tree.n_chunks - 1, buf);
+  NXFX_LAUNCH(ctx, (tree_top_kernel<true, kFinish>), 1, kTreeThreads, tree_smem_bytes(ctx->tree.cap), make_tree(ctx), ctx->tree.n_chunks - 1, buf);
   ctx->pc_ready = true;
   return NXFX_OK;
 }
@@ -1058,8 +1062,8 @@ int nxfx_pc_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
     NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->edge_g.p, ctx->edge_c.p,
                 ctx->edge_fn.p, ctx->lam_weight.p);
   }
-  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
-  NXFX_LAUNCH(ctx, (tree_top_kernel<false, kPartial>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, nb, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, ctx->ticket.p + 1, 0);
+  NXFX_LAUNCH(ctx, (tree_top_kernel<false, kPartial>), 1, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, buf);
   return NXFX_OK;
 }
 
@@ -1070,8 +1074,8 @@ int nxfx_pc_apply_end(nxfx_ctx* ctx, const double* r, double* z, double* buf, in
   Net g = make_net(ctx);
   TreeDev t = make_tree(ctx);
   const int nb = ctx->tree.n_chunks - 1;
-  NXFX_LAUNCH(ctx, (tree_top_kernel<false, kFinish>), 1, kTreeThreads, sizeof(TreeSmem), t, nb, buf);
-  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, sizeof(TreeSmem), t, nb, ctx->ticket.p + 1, 0);
+  NXFX_LAUNCH(ctx, (tree_top_kernel<false, kFinish>), 1, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, buf);
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, ctx->ticket.p + 1, 0);
   const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
   if (ctx->N == 1) {
     if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);

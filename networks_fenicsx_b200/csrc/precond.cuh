@@ -38,6 +38,7 @@ struct TreeDev {
   double* r;
   double* lam;      // schedule order
   double* lam_nat;  // natural (bifurcation) order, read by the back-substitution
+  int cap;          // chunk capacity of the shared-memory sweeps (2048 or 4096)
 };
 
 // N == 1 fusion: the tree kernels can evaluate a node's Laplacian diagonal / right-hand side on the
@@ -153,25 +154,45 @@ tree_sweep_kernel(TreeDev t, const double* __restrict__ edge_g, int chunk0) {
 // are co-resident (cooperative launch): they wait on an epoch flag for the top chunk and then
 // back-substitute their chunk straight from shared memory -- one launch per preconditioner
 // application.  Trees with more chunks than resident blocks use two launches (up, down).
-constexpr int kChunkCap = 2048;  // nodes per chunk held in shared memory
-constexpr int kLevelCap = 64;    // levels per chunk held in shared memory
-constexpr int kChildCap = 4096;  // child links per chunk (the top chunk also lists its bottom-chunk children)
+// Chunk capacity is a launch-time parameter (TreeDev::cap): 2048 nodes per chunk keeps two blocks
+// resident per SM (single-launch cooperative solve up to ~20 generations of a binary tree); 4096
+// is selected by the schedule builder when the top chunk would not fit otherwise (24-25
+// generations, > 100 M DOFs).  Child links: 2 * cap (the top chunk also lists its bottom-chunk children).
+constexpr int kChunkCapMax = 4096;
+constexpr int kLevelCap = 64;  // levels per chunk held in shared memory
 constexpr int kDescInts = 8 + kLevelCap + 1;  // {b0, b1, cb, ce, nl, Lw, -, -, lvl[0..nl]}
 #ifndef NXFX_TREE_THREADS
 #define NXFX_TREE_THREADS 1024
 #endif
 constexpr int kTreeThreads = NXFX_TREE_THREADS;
 
-struct TreeSmem {
-  double a[kChunkCap];  // F: d -> 1/d   solve: r -> lam
-  double b[kChunkCap];  // F: tg         solve: 1/d
-  double c[kChunkCap];  // F: gd         solve: gd
-  int cptr[kChunkCap + 1];
-  int cidx[kChildCap];
-  int par[kChunkCap];
-  int lvl[kLevelCap + 1];
-  int last;
+struct TreeSmem {  // view of the dynamic shared memory of a tree kernel
+  double* a;  // F: d -> 1/d   solve: r -> lam      [cap]
+  double* b;  // F: tg         solve: 1/d           [cap]
+  double* c;  // F: gd         solve: gd            [cap]
+  int* cptr;  // [cap + 4]
+  int* cidx;  // [2 cap]
+  int* par;   // [cap]
+  int* lvl;   // [kLevelCap + 3]
+  int* last;
 };
+
+__host__ __device__ constexpr size_t tree_smem_bytes(int cap) {
+  return (size_t)cap * (3 * sizeof(double) + 4 * sizeof(int)) + (size_t)(4 + kLevelCap + 3 + 1) * sizeof(int);
+}
+
+__device__ __forceinline__ TreeSmem tree_view(unsigned char* raw, int cap) {
+  TreeSmem S;
+  S.a = reinterpret_cast<double*>(raw);
+  S.b = S.a + cap;
+  S.c = S.b + cap;
+  S.cptr = reinterpret_cast<int*>(S.c + cap);
+  S.cidx = S.cptr + cap + 4;
+  S.par = S.cidx + 2 * cap;
+  S.lvl = S.par + cap;
+  S.last = S.lvl + kLevelCap + 3;
+  return S;
+}
 
 enum { kTreeFactor = 0, kTreeUp = 1, kTreeDown = 2 };
 
@@ -179,7 +200,7 @@ struct ChunkInfo {
   int b0, b1, cb, ce, nl, Lw;  // Lw: levels 0..Lw all have <= 32 nodes (warp phase), -1 if none
 };
 
-__device__ __forceinline__ ChunkInfo load_chunk_info(const TreeDev& t, int chunk, TreeSmem& S) {
+__device__ __forceinline__ ChunkInfo load_chunk_info(const TreeDev& t, int chunk, const TreeSmem& S) {
   const int32_t* __restrict__ desc = t.chunk_desc + (size_t)chunk * kDescInts;
   ChunkInfo ci{desc[0], desc[1], desc[2], desc[3], desc[4], desc[5]};
   for (int i = threadIdx.x; i <= ci.nl; i += blockDim.x) S.lvl[i] = desc[8 + i];
@@ -220,7 +241,7 @@ __device__ __forceinline__ void sweep_down(const TreeSmem& S, const ChunkInfo& c
   }
 }
 
-__device__ __forceinline__ void load_children(const TreeDev& t, const ChunkInfo& ci, TreeSmem& S) {
+__device__ __forceinline__ void load_children(const TreeDev& t, const ChunkInfo& ci, const TreeSmem& S) {
   const int nn = ci.b1 - ci.b0;
   for (int i = threadIdx.x; i <= nn; i += blockDim.x) S.cptr[i] = t.t_cptr[ci.b0 + i] - ci.cb;
   for (int i = threadIdx.x; i < ci.ce - ci.cb; i += blockDim.x) S.cidx[i] = t.t_cidx[ci.cb + i];
@@ -234,7 +255,7 @@ enum { kFull = 0, kPartial = 1, kFinish = 2 };
 // numeric factorisation of one chunk: d_n = diag0_n - sum_c tg_c * gd_c, gd_n = tg_n / d_n;
 // t.d receives 1/d.  `top`: children below b0 live in bottom chunks (already written to HBM).
 // buf (top chunk, kPartial/kFinish): [partial d | tg], 2*nn doubles.
-__device__ __forceinline__ void factor_chunk(const TreeDev& t, TreeSmem& S, int chunk, bool top,
+__device__ __forceinline__ void factor_chunk(const TreeDev& t, const TreeSmem& S, int chunk, bool top,
                                              int phase = kFull, double* buf = nullptr,
                                              const FusedN1* f = nullptr) {
   const ChunkInfo ci = load_chunk_info(t, chunk, S);
@@ -286,7 +307,7 @@ __device__ __forceinline__ void factor_chunk(const TreeDev& t, TreeSmem& S, int 
 }
 
 // stage a chunk for the solve: a = r, b = 1/d, c = gd, par
-__device__ __forceinline__ void load_solve_chunk(const TreeDev& t, const ChunkInfo& ci, TreeSmem& S,
+__device__ __forceinline__ void load_solve_chunk(const TreeDev& t, const ChunkInfo& ci, const TreeSmem& S,
                                                  const FusedN1* f = nullptr) {
   const int nn = ci.b1 - ci.b0;
   for (int i = threadIdx.x; i < nn; i += blockDim.x) {
@@ -297,7 +318,7 @@ __device__ __forceinline__ void load_solve_chunk(const TreeDev& t, const ChunkIn
   }
 }
 
-__device__ __forceinline__ void solve_up(const TreeDev& t, TreeSmem& S, const ChunkInfo& ci, bool top,
+__device__ __forceinline__ void solve_up(const TreeDev& t, const TreeSmem& S, const ChunkInfo& ci, bool top,
                                          int phase = kFull, double* buf = nullptr) {
   const int b0 = ci.b0, nn = ci.b1 - ci.b0;
   if (phase == kFinish) {
@@ -331,7 +352,7 @@ __device__ __forceinline__ void solve_up(const TreeDev& t, TreeSmem& S, const Ch
 }
 
 // lam = r/d + gd * lam(parent); parents outside the chunk (top chunk) are read through L2
-__device__ __forceinline__ void solve_down(const TreeDev& t, TreeSmem& S, const ChunkInfo& ci) {
+__device__ __forceinline__ void solve_down(const TreeDev& t, const TreeSmem& S, const ChunkInfo& ci) {
   const int b0 = ci.b0, b1 = ci.b1, nn = ci.b1 - ci.b0;
   sweep_down(S, ci, [&](int n) {
     const int i = n - b0;
@@ -348,20 +369,21 @@ __device__ __forceinline__ void solve_down(const TreeDev& t, TreeSmem& S, const 
 }
 
 // true in the block that finished last
-__device__ __forceinline__ bool last_block_done(TreeSmem& S, unsigned int* ticket, int n_bottom) {
+__device__ __forceinline__ bool last_block_done(const TreeSmem& S, unsigned int* ticket, int n_bottom) {
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) S.last = (atomicAdd(ticket, 1u) == (unsigned int)n_bottom - 1);
+  if (threadIdx.x == 0) *S.last = (atomicAdd(ticket, 1u) == (unsigned int)n_bottom - 1);
   __syncthreads();
-  if (S.last) __threadfence();
-  return S.last;
+  const bool last = *S.last != 0;
+  if (last) __threadfence();
+  return last;
 }
 
 // grid = max(n_bottom, 1); do_top = 0 (multi-GPU): bottom chunks only
 __global__ void __launch_bounds__(kTreeThreads)
 tree_factor_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top, FusedN1 fin) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
-  TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
+  TreeSmem S = tree_view(tree_smem_raw, t.cap);
   const FusedN1* f = fin.cell_rh ? &fin : nullptr;
   if (n_bottom > 0) {
     factor_chunk(t, S, blockIdx.x, false, kFull, nullptr, f);
@@ -382,7 +404,7 @@ template <bool FACTOR, int PHASE>
 __global__ void __launch_bounds__(kTreeThreads)
 tree_top_kernel(TreeDev t, int top_chunk, double* buf) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
-  TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
+  TreeSmem S = tree_view(tree_smem_raw, t.cap);
   if (FACTOR) {
     factor_chunk(t, S, top_chunk, true, PHASE, buf);
   } else {
@@ -399,7 +421,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kTreeThreads)
 tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
-  TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
+  TreeSmem S = tree_view(tree_smem_raw, t.cap);
   if (MODE == kTreeDown) {
     const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
     load_solve_chunk(t, ci, S);
@@ -432,7 +454,7 @@ __global__ void __launch_bounds__(kTreeThreads)
 tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch,
                        FusedN1 fin) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
-  TreeSmem& S = *reinterpret_cast<TreeSmem*>(tree_smem_raw);
+  TreeSmem S = tree_view(tree_smem_raw, t.cap);
   const FusedN1* f = fin.r ? &fin : nullptr;
   const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
   load_children(t, ci, S);

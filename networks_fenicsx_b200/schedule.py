@@ -176,4 +176,16 @@ def build_tree_schedule(edges: np.ndarray, node_lm: np.ndarray, n_bif: int,
         return TreeSchedule(z, z, z, np.zeros(1, dtype=i32), z, np.zeros(1, dtype=i32), np.zeros(1, dtype=i32), z, z)
     parent, pedge, depth, chord = spanning_forest(edges, node_lm, n_bif, root_hint_nodes)
     chunk, n_chunks = assign_chunks(parent, depth, chunk_nodes)
-    return assemble_schedule(parent, pedge, depth, chunk, n_chunks, chord)
+    sched = assemble_schedule(parent, pedge, depth, chunk, n_chunks, chord)
+    if chunk_nodes == CHUNK_NODES and _top_size(sched) > CHUNK_NODES:
+        # very large trees: the top chunk outgrows a 2048-node block; 4096-node chunks halve it
+        # (the device kernels accept both capacities)
+        chunk, n_chunks = assign_chunks(parent, depth, 2 * CHUNK_NODES)
+        bigger = assemble_schedule(parent, pedge, depth, chunk, n_chunks, chord)
+        if _top_size(bigger) <= 2 * CHUNK_NODES:
+            sched = bigger
+    return sched
+
+
+def _top_size(s: TreeSchedule) -> int:
+    return int(s.lvl_ptr[s.chunk_lptr[-1]] - s.lvl_ptr[s.chunk_lptr[-2]])
