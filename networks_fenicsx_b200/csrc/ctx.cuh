@@ -40,7 +40,8 @@ struct TreeSchedule {
   bool set = false;
   int n_chunks = 0, n_lvl_ptr = 0, n_chords = 0, n_top = 0;
   int cap = 2048;  // chunk capacity of the shared-memory sweeps
-  DevBuf<int32_t> bif_of_t, chunk_desc;
+  DevBuf<int32_t> bif_of_t, chunk_desc, t_inc_ptr;
+  DevBuf<int2> t_inc;
   DevBuf<double> lam_nat;
   DevBuf<int32_t> t_of_bif, t_parent, t_pedge, t_cptr, t_cidx, chunk_lptr, lvl_ptr, chord_edge;
   // numeric

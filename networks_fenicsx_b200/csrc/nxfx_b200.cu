@@ -46,6 +46,8 @@ TreeDev make_tree(nxfx_ctx* c) {
   t.t_of_bif = s.t_of_bif.p;
   t.bif_of_t = s.bif_of_t.p;
   t.chunk_desc = s.chunk_desc.p;
+  t.t_inc_ptr = s.t_inc_ptr.p;
+  t.t_inc = s.t_inc.p;
   t.lam_nat = s.lam_nat.p;
   t.cap = s.cap;
   t.t_parent = s.t_parent.p;
@@ -770,6 +772,21 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
   }
   if ((rc = upload(ctx, s.bif_of_t, inv.data(), nb))) return rc;
   NXFX_CUDA(ctx, s.lam_nat.alloc(nb));
+  {  // incidences of every node in schedule order (read by the fused N == 1 tree kernels)
+    DevBuf<int32_t> len;
+    NXFX_CUDA(ctx, len.alloc(nb + 1));
+    NXFX_CUDA(ctx, s.t_inc_ptr.alloc(nb + 1));
+    NXFX_CUDA(ctx, s.t_inc.alloc((size_t)std::max(ctx->n_inc, 1)));
+    NXFX_LAUNCH(ctx, t_inc_len_kernel, (int)cdiv(nb + 1, kThreads), kThreads, 0, (int)nb, s.bif_of_t.p, ctx->bif_ptr.p, len.p);
+    size_t tmp_bytes = 0;
+    NXFX_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len.p, s.t_inc_ptr.p, (int)nb + 1, ctx->stream));
+    DevBuf<char> tmp;
+    NXFX_CUDA(ctx, tmp.alloc(tmp_bytes));
+    NXFX_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, len.p, s.t_inc_ptr.p, (int)nb + 1, ctx->stream));
+    NXFX_LAUNCH(ctx, t_inc_fill_kernel, (int)cdiv(nb, kThreads), kThreads, 0, (int)nb, s.bif_of_t.p, ctx->bif_ptr.p,
+                ctx->bif_inc.p, ctx->edge_slot.p, s.t_inc_ptr.p, s.t_inc.p);
+    NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   if ((rc = upload(ctx, s.t_parent, t_parent, nb))) return rc;
   if ((rc = upload(ctx, s.t_pedge, t_pedge, nb))) return rc;
   if ((rc = upload(ctx, s.t_cptr, t_cptr, nb + 1))) return rc;

@@ -31,6 +31,8 @@ struct TreeDev {
   const int32_t* __restrict__ chunk_lptr;
   const int32_t* __restrict__ lvl_ptr;
   const int32_t* __restrict__ chunk_desc;  // [n_chunks][kDescInts]: {b0, b1, cb, ce, nl, lvl[0..nl]}
+  const int32_t* __restrict__ t_inc_ptr;   // incidences of every node in SCHEDULE order (N == 1 fusion)
+  const int2* __restrict__ t_inc;          // {2 * flux slot | is_in, graph edge}
   double* diag0;
   double* tg;  // conductance of the link to the parent (0 for roots)
   double* d;
@@ -50,24 +52,46 @@ struct FusedN1 {
   const double* cell_rh;
 };
 
-__device__ __forceinline__ double n1_bif_rhs(const FusedN1& f, int bi) {
-  const Net& g = f.g;
-  double s = -f.r[g.loff + bi];
-  for (int k = g.bif_ptr[bi]; k < g.bif_ptr[bi + 1]; ++k) {
-    const int inc = g.bif_inc[k], e = inc >> 1;
-    const double2 rq = *reinterpret_cast<const double2*>(f.r + 2 * (size_t)g.edge_slot[e]);
-    const double rp = f.r[g.poff + e], rh = f.cell_rh[e];
+// n = node in schedule order; its incidences come from the schedule-ordered table (two dependent
+// loads instead of the five of bif_of_t -> bif_ptr -> bif_inc -> edge_slot -> r)
+__device__ __forceinline__ double n1_node_rhs(const FusedN1& f, const TreeDev& t, int n) {
+  double s = -f.r[f.g.loff + t.bif_of_t[n]];
+  for (int k = t.t_inc_ptr[n]; k < t.t_inc_ptr[n + 1]; ++k) {
+    const int2 inc = t.t_inc[k];
+    const double2 rq = *reinterpret_cast<const double2*>(f.r + (inc.x & ~1));
+    const double rp = f.r[f.g.poff + inc.y], rh = f.cell_rh[inc.y];
     const double gc = ((rq.x + rq.y) - 0.5 * rh * rp) / rh;
-    s += (inc & 1) ? (rp + gc) : -gc;
+    s += (inc.x & 1) ? (rp + gc) : -gc;
   }
   return s;
 }
 
-__device__ __forceinline__ double n1_bif_diag(const FusedN1& f, int bi) {
-  const Net& g = f.g;
+__device__ __forceinline__ double n1_node_diag(const FusedN1& f, const TreeDev& t, int n) {
   double s = 0.0;
-  for (int k = g.bif_ptr[bi]; k < g.bif_ptr[bi + 1]; ++k) s += 1.0 / f.cell_rh[g.bif_inc[k] >> 1];
+  for (int k = t.t_inc_ptr[n]; k < t.t_inc_ptr[n + 1]; ++k) s += 1.0 / f.cell_rh[t.t_inc[k].y];
   return s;
+}
+
+// schedule-ordered incidence table (built once per schedule)
+__global__ void __launch_bounds__(kThreads)
+t_inc_len_kernel(int n_bif, const int32_t* __restrict__ bif_of_t, const int32_t* __restrict__ bif_ptr,
+                 int32_t* __restrict__ len) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n > n_bif) return;
+  len[n] = n < n_bif ? bif_ptr[bif_of_t[n] + 1] - bif_ptr[bif_of_t[n]] : 0;
+}
+__global__ void __launch_bounds__(kThreads)
+t_inc_fill_kernel(int n_bif, const int32_t* __restrict__ bif_of_t, const int32_t* __restrict__ bif_ptr,
+                  const int32_t* __restrict__ bif_inc, const int32_t* __restrict__ edge_slot,
+                  const int32_t* __restrict__ t_inc_ptr, int2* __restrict__ t_inc) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_bif) return;
+  const int bi = bif_of_t[n];
+  int o = t_inc_ptr[n];
+  for (int k = bif_ptr[bi]; k < bif_ptr[bi + 1]; ++k, ++o) {
+    const int inc = bif_inc[k], e = inc >> 1;
+    t_inc[o] = make_int2(2 * edge_slot[e] | (inc & 1), e);
+  }
 }
 
 // g_e = 1 / sum_j R_j h_j
@@ -265,7 +289,7 @@ __device__ __forceinline__ void factor_chunk(const TreeDev& t, const TreeSmem& S
     for (int i = tid; i < nn; i += nth) { S.a[i] = buf[i]; S.b[i] = buf[nn + i]; }
   } else if (f) {
     for (int i = tid; i < nn; i += nth) {
-      S.a[i] = n1_bif_diag(*f, t.bif_of_t[b0 + i]);
+      S.a[i] = n1_node_diag(*f, t, b0 + i);
       const int pe = t.t_pedge[b0 + i];
       const double tg = pe >= 0 ? 1.0 / f->cell_rh[pe] : 0.0;
       S.b[i] = tg;
@@ -311,7 +335,7 @@ __device__ __forceinline__ void load_solve_chunk(const TreeDev& t, const ChunkIn
                                                  const FusedN1* f = nullptr) {
   const int nn = ci.b1 - ci.b0;
   for (int i = threadIdx.x; i < nn; i += blockDim.x) {
-    S.a[i] = f ? n1_bif_rhs(*f, t.bif_of_t[ci.b0 + i]) : t.r[ci.b0 + i];
+    S.a[i] = f ? n1_node_rhs(*f, t, ci.b0 + i) : t.r[ci.b0 + i];
     S.b[i] = t.d[ci.b0 + i];
     S.c[i] = t.gd[ci.b0 + i];
     S.par[i] = t.t_parent[ci.b0 + i];
