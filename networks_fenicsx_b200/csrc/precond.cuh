@@ -473,8 +473,9 @@ tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top) {
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
-// single-launch solve: requires all n_bottom blocks to be co-resident (cooperative launch)
-__global__ void __launch_bounds__(kTreeThreads)
+// single-launch solve: requires all n_bottom blocks to be co-resident (cooperative launch); two
+// blocks per SM (<= 32 registers) so that 20 generations (256 bottom chunks) fit 148 SMs
+__global__ void __launch_bounds__(kTreeThreads, 2)
 tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch,
                        FusedN1 fin) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];

@@ -269,6 +269,17 @@ def test_full_size_properties():
     lu = net.lm_index[net.edges[:, 0]]
     pu = np.where(lu >= 0, lam[np.maximum(lu, 0)], -net.eval_pbc(P_Y)[net.edges[:, 0]])
     np.testing.assert_allclose(x[nq:nq + nc], pu - q_edge * h / 2, rtol=1e-8, atol=1e-11)
+    # the headline step is five launches: assembly, factorisation (diagonals fused), single-launch
+    # cooperative tree solve (right-hand sides fused), back-substitution, residual.  A silently
+    # disabled cooperative path (e.g. register growth -> one block per SM) shows up here as seven.
+    fast = nxfx.Solver(asm, schedule=solver._schedule)
+    fast.assemble()
+    fast.solve()
+    dev = nm.device
+    l0 = dev.launch_count
+    fast.assemble()
+    fast.solve()
+    assert dev.launch_count - l0 == 5
 
 
 def _graph(points, edges):
