@@ -48,6 +48,7 @@ struct TreeSchedule {
   DevBuf<double> diag0, tg, d, gd, r, lam;  // schedule order
   bool fast_ok = false;                       // every chunk fits the shared-memory sweep kernel
   bool coop_ok = false;                       // all bottom chunks can be co-resident (single-launch solve)
+  bool coop_fs_ok = false;                    // ... also with the larger buffers of the fused factor + solve
   unsigned int epoch = 0;
 };
 

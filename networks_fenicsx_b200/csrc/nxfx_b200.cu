@@ -255,6 +255,34 @@ int do_pc_setup(nxfx_ctx* ctx) {
   return NXFX_OK;
 }
 
+// factorisation and first application z = P^{-1} r in one cooperative launch (N == 1, single GPU)
+bool can_fuse_setup(const nxfx_ctx* ctx) {
+  return ctx->N == 1 && ctx->tree.set && ctx->tree.fast_ok && ctx->tree.coop_fs_ok && ctx->n_bif > 0 &&
+         ctx->tree.n_chunks > 1 && !ctx->lam_weight.p;
+}
+
+int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z) {
+  NXFX_REQUIRE(ctx, ctx->assembled, "assemble the matrix before pc_setup");
+  NXFX_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(r) & 15) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0,
+               "vectors must be 16-byte aligned");
+  auto& s = ctx->tree;
+  Net g = make_net(ctx);
+  TreeDev t = make_tree(ctx);
+  FusedN1 fin{g, r, ctx->cell_rh.p};
+  unsigned int* tk = ctx->ticket.p + 1;
+  unsigned int* fl = ctx->ticket.p + 2;
+  unsigned int ep = ++s.epoch;
+  int nb = s.n_chunks - 1;
+  void* args[] = {&t, &nb, &tk, &fl, &ep, &fin};
+  NXFX_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tree_factor_solve_coop_kernel), dim3(nb),
+                                             dim3(kTreeThreads), args, tree_smem_bytes_fs(s.cap), ctx->stream));
+  ctx->launches++;
+  ctx->pc_ready = true;
+  const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
+  NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+  return NXFX_OK;
+}
+
 int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add = false) {
   const int n = (int)ctx->ndofs;
   if (add && pc_type != NXFX_PC_NETWORK_SCHUR) {  // generic: z_tmp = P^{-1} r, z += z_tmp
@@ -332,12 +360,13 @@ void push_history(nxfx_solve_info* info, double v) {
 // its norms: the common case (first solve already converged) costs one SpMV and no extra launch.
 // refine_rtol = 0 forces every allowed correction.  The reported residual is the last one computed;
 // final_residual adds an evaluation after the last correction.
-int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts* o, nxfx_solve_info* info) {
+int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts* o, nxfx_solve_info* info,
+                  bool fused_setup) {
   int rc = ensure_work(ctx, 3);
   if (rc) return rc;
   double* r = ctx->work.p;
   const int steps = std::max(0, std::min(o->refine_steps, 32));
-  if ((rc = do_pc_apply(ctx, o->pc_type, b, x, false))) return rc;
+  if ((rc = fused_setup ? do_pc_setup_apply(ctx, b, x) : do_pc_apply(ctx, o->pc_type, b, x, false))) return rc;
   info->iterations = 1;
   if (steps == 0 && !o->final_residual) {  // plain preconditioner application, nothing measured
     NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -829,6 +858,14 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_solve_coop_kernel, kTreeThreads, tree_smem_bytes(ctx->tree.cap)) == cudaSuccess)
       s.coop_ok = (n_chunks - 1) <= per_sm * ctx->sm_count;
     cudaGetLastError();
+    s.coop_fs_ok = false;
+    per_sm = 0;
+    if (s.coop_ok && cudaFuncSetAttribute(tree_factor_solve_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)tree_smem_bytes_fs(kChunkCapMax)) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_factor_solve_coop_kernel, kTreeThreads,
+                                                      tree_smem_bytes_fs(ctx->tree.cap)) == cudaSuccess)
+      s.coop_fs_ok = (n_chunks - 1) <= per_sm * ctx->sm_count;
+    cudaGetLastError();
     NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));
     NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<true, kPartial>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));
     NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<true, kFinish>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));
@@ -885,9 +922,13 @@ int nxfx_solve(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts*
   int rc;
   if (opts->pc_type == NXFX_PC_NETWORK_SCHUR && ctx->generic)
     return fail(ctx, NXFX_ERR_UNSUPPORTED, "the network Schur preconditioner is implemented for flux P1 / pressure DG0");
-  if (opts->pc_type == NXFX_PC_NETWORK_SCHUR && !ctx->pc_ready)
-    if ((rc = do_pc_setup(ctx))) return rc;
-  if (opts->ksp_type == NXFX_KSP_PREONLY) rc = solve_preonly(ctx, b, x, opts, info);
+  bool fused_setup = false;
+  if (opts->pc_type == NXFX_PC_NETWORK_SCHUR && !ctx->pc_ready) {
+    // a fresh matrix and a direct solve: factorise while eliminating the right-hand side
+    fused_setup = opts->ksp_type == NXFX_KSP_PREONLY && can_fuse_setup(ctx);
+    if (!fused_setup && (rc = do_pc_setup(ctx))) return rc;
+  }
+  if (opts->ksp_type == NXFX_KSP_PREONLY) rc = solve_preonly(ctx, b, x, opts, info, fused_setup);
   else if (opts->ksp_type == NXFX_KSP_FGMRES) rc = solve_fgmres(ctx, b, x, opts, info);
   else return fail(ctx, NXFX_ERR_UNSUPPORTED, "unknown ksp_type %d", opts->ksp_type);
   if (rc) return rc;

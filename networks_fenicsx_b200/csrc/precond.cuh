@@ -520,6 +520,99 @@ tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned i
   solve_down(t, S, ci);
 }
 
+// ---- factorisation fused with the first solve (N == 1, single GPU) --------------------------------
+// The leaf -> root sweep of the factorisation and the forward elimination of the first right-hand
+// side visit the same nodes in the same order: one staging pass, one set of level barriers.  A fourth
+// shared array e = tg sits behind the TreeSmem view (the parent needs tg_c and gd_c of its children).
+// Arithmetic per node is exactly that of factor_chunk + solve_up.
+__host__ __device__ constexpr size_t tree_smem_bytes_fs(int cap) {
+  return ((tree_smem_bytes(cap) + 15) & ~(size_t)15) + (size_t)cap * sizeof(double);
+}
+
+__device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem& S, double* __restrict__ Se,
+                                                const ChunkInfo& ci, bool top, const FusedN1& f) {
+  const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
+  for (int i = tid; i < nn; i += nth) {
+    S.a[i] = n1_node_rhs(f, t, b0 + i);
+    S.b[i] = n1_node_diag(f, t, b0 + i);
+    const int pe = t.t_pedge[b0 + i];
+    const double tg = pe >= 0 ? 1.0 / f.cell_rh[pe] : 0.0;
+    Se[i] = tg;
+    t.tg[b0 + i] = tg;
+    S.par[i] = t.t_parent[b0 + i];
+  }
+  __syncthreads();
+  if (top) {  // fold in the bottom-chunk children (written by the other blocks of this launch)
+    for (int i = tid; i < nn; i += nth) {
+      double ad = S.b[i], ar = S.a[i];
+      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+        const int c = S.cidx[k];
+        if (c < b0) {
+          const double gdc = __ldcg(t.gd + c);
+          ad -= __ldcg(t.tg + c) * gdc;
+          ar += gdc * __ldcg(t.r + c);
+        }
+      }
+      S.b[i] = ad;
+      S.a[i] = ar;
+    }
+    __syncthreads();
+  }
+  sweep_up(S, ci, [&](int n) {
+    const int i = n - b0;
+    double ad = S.b[i], ar = S.a[i];
+    for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+      const int c = S.cidx[k] - b0;
+      if (c >= 0) {
+        ad -= Se[c] * S.c[c];
+        ar += S.c[c] * S.a[c];
+      }
+    }
+    const double inv = 1.0 / ad;
+    S.b[i] = inv;
+    S.c[i] = Se[i] * inv;
+    S.a[i] = ar;
+  });
+  for (int i = tid; i < nn; i += nth) { t.d[b0 + i] = S.b[i]; t.gd[b0 + i] = S.c[i]; }
+}
+
+__global__ void __launch_bounds__(kTreeThreads, 2)
+tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch,
+                              FusedN1 fin) {
+  extern __shared__ __align__(16) unsigned char tree_smem_raw[];
+  TreeSmem S = tree_view(tree_smem_raw, t.cap);
+  double* Se = reinterpret_cast<double*>(tree_smem_raw + ((tree_smem_bytes(t.cap) + 15) & ~(size_t)15));
+  const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
+  load_children(t, ci, S);
+  factor_solve_up(t, S, Se, ci, false, fin);
+  // the eliminated right-hand side of the whole chunk goes to HBM: later solves reuse the factors,
+  // the top chunk reads the roots, and the last block recycles its staging buffer
+  for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x) t.r[ci.b0 + i] = S.a[i];
+  if (last_block_done(S, ticket, n_bottom)) {
+    const ChunkInfo ti = load_chunk_info(t, n_bottom, S);
+    load_children(t, ti, S);
+    factor_solve_up(t, S, Se, ti, true, fin);
+    solve_down(t, S, ti);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *ticket = 0u;
+      __threadfence();
+      atomicExch(flag, epoch);
+    }
+    load_chunk_info(t, blockIdx.x, S);
+    load_solve_chunk(t, ci, S);
+    __syncthreads();
+  } else {
+    if (threadIdx.x == 0) {
+      while (atomicAdd(flag, 0u) != epoch) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  solve_down(t, S, ci);
+}
+
 // Edge condensation: c_e = sum r_q - w.F,  F_N = sum r_p
 __global__ void __launch_bounds__(kThreads)
 edge_condense_kernel(Net g, const double* __restrict__ cell_rh, const double* __restrict__ r,

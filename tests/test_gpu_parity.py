@@ -269,9 +269,9 @@ def test_full_size_properties():
     lu = net.lm_index[net.edges[:, 0]]
     pu = np.where(lu >= 0, lam[np.maximum(lu, 0)], -net.eval_pbc(P_Y)[net.edges[:, 0]])
     np.testing.assert_allclose(x[nq:nq + nc], pu - q_edge * h / 2, rtol=1e-8, atol=1e-11)
-    # the headline step is five launches: assembly, factorisation (diagonals fused), single-launch
-    # cooperative tree solve (right-hand sides fused), back-substitution, residual.  A silently
-    # disabled cooperative path (e.g. register growth -> one block per SM) shows up here as seven.
+    # the headline step is four launches: assembly, one cooperative tree kernel (factorisation fused
+    # with the first solve), back-substitution, residual.  A silently disabled cooperative path
+    # (e.g. register growth -> one block per SM) shows up here as five or seven.
     fast = nxfx.Solver(asm, schedule=solver._schedule)
     fast.assemble()
     fast.solve()
@@ -279,7 +279,10 @@ def test_full_size_properties():
     l0 = dev.launch_count
     fast.assemble()
     fast.solve()
-    assert dev.launch_count - l0 == 5
+    assert dev.launch_count - l0 == 4
+    x_fused = np.concatenate([f.x.array for f in fast.solve()])  # factors reused: separate solve kernel
+    assert dev.launch_count - l0 == 7
+    assert helpers.rel_l2(x_fused, x) < 1e-12
 
 
 def _graph(points, edges):
