@@ -82,7 +82,8 @@ int ensure_scal(nxfx_ctx* ctx) {
   NXFX_CUDA(ctx, cudaMemsetAsync(ctx->scal.p, 0, (kScalPartials + kScalSlots) * sizeof(double), ctx->stream));
   NXFX_CUDA(ctx, ctx->ticket.alloc(4));
   NXFX_CUDA(ctx, cudaMemsetAsync(ctx->ticket.p, 0, 4 * sizeof(unsigned int), ctx->stream));
-  NXFX_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->scal_h), kScalSlots * sizeof(double), cudaHostAllocDefault));
+  NXFX_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->scal_h), kScalSlots * sizeof(double), cudaHostAllocMapped));
+  NXFX_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->scal_h_dev), ctx->scal_h, 0));
   return NXFX_OK;
 }
 
@@ -377,8 +378,8 @@ int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_op
   const double rt = o->refine_rtol > 0.0 ? o->refine_rtol : 0.0;
   int applied = 0;
   while (true) {
-    if ((rc = do_residual(ctx, b, x, r, slot(ctx, 0)))) return rc;
-    NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, slot(ctx, 0), 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    // the reducing block stores the two norms straight into mapped pinned memory: no copy-engine hop
+    if ((rc = do_residual(ctx, b, x, r, ctx->scal_h_dev))) return rc;
     NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     info->rhs_norm = std::sqrt(ctx->scal_h[1]);
     info->residual_norm = std::sqrt(ctx->scal_h[0]);
