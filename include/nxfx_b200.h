@@ -218,6 +218,10 @@ int nxfx_assemble_generic(nxfx_ctx* ctx, const double* R_cell_d, double R_const,
  *                        right after nxfx_pc_setup_begin with a second buffer: setup and first
  *                        application then share ONE all-reduce, followed by _setup_end, _apply_end)
  *   nxfx_pc_apply_end    <- all-reduced buf: top solve, back-substitution; z = or += P^{-1} r
+ *   nxfx_pc_setup_apply_begin / _end  the recommended form of that fused sequence: buf = 3*n_top
+ *                        doubles [partial pivots | link conductances | partial right-hand side],
+ *                        one all-reduce in between, z = P^{-1} r.  With one cell per edge the
+ *                        bottom chunks are factorised WHILE their right-hand sides are eliminated.
  *   nxfx_pack_shared / nxfx_unpack_shared  shared multiplier rows of a vector <-> buf (after
  *                        y = A x these rows are partial sums)
  *   nxfx_norm2_owned     out_d[0] = sum of squares over the entries this rank owns (async)
@@ -232,6 +236,8 @@ int nxfx_pc_setup_begin(nxfx_ctx* ctx, double* buf_d);
 int nxfx_pc_setup_end(nxfx_ctx* ctx, double* buf_d);
 int nxfx_pc_apply_begin(nxfx_ctx* ctx, const double* r_d, double* buf_d);
 int nxfx_pc_apply_end(nxfx_ctx* ctx, const double* r_d, double* z_d, double* buf_d, int add);
+int nxfx_pc_setup_apply_begin(nxfx_ctx* ctx, const double* r_d, double* buf_d);
+int nxfx_pc_setup_apply_end(nxfx_ctx* ctx, const double* r_d, double* z_d, double* buf_d);
 int nxfx_pack_shared(nxfx_ctx* ctx, const double* v_d, double* buf_d);
 int nxfx_unpack_shared(nxfx_ctx* ctx, const double* buf_d, double* v_d);
 int nxfx_norm2_owned(nxfx_ctx* ctx, const double* v_d, double* out_d);

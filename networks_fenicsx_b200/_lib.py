@@ -118,6 +118,8 @@ SIGNATURES = {
     "nxfx_pc_setup_end": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nxfx_pc_apply_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nxfx_pc_apply_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "nxfx_pc_setup_apply_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nxfx_pc_setup_apply_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nxfx_pack_shared": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nxfx_unpack_shared": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nxfx_norm2_owned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

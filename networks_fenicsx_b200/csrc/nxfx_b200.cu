@@ -496,6 +496,7 @@ int setup_spmv_tiles(nxfx_ctx* ctx) {
   if (ctx->pipe_ok) {
     NXFX_CUDA(ctx, cudaFuncSetAttribute(spmv_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
     NXFX_CUDA(ctx, cudaFuncSetAttribute(spmv_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(spmv_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
   }
   return NXFX_OK;
 }
@@ -859,6 +860,9 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_solve_coop_kernel, kTreeThreads, tree_smem_bytes(ctx->tree.cap)) == cudaSuccess)
       s.coop_ok = (n_chunks - 1) <= per_sm * ctx->sm_count;
     cudaGetLastError();
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_factor_solve_bottom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes_fs(kChunkCapMax)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_top_fs_kernel<kPartial>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes_fs(kChunkCapMax)));
+    NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_top_fs_kernel<kFinish>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes_fs(kChunkCapMax)));
     s.coop_fs_ok = false;
     per_sm = 0;
     if (s.coop_ok && cudaFuncSetAttribute(tree_factor_solve_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1148,6 +1152,54 @@ int nxfx_pc_apply_end(nxfx_ctx* ctx, const double* r, double* z, double* buf, in
   return NXFX_OK;
 }
 
+// setup + first application in one pair of calls around ONE all-reduce of 3*n_top doubles.
+// N == 1: the bottom chunks are factorised while their right-hand sides are eliminated (one kernel),
+// the top chunk handles factor and solve together in each phase; otherwise the four separate phases.
+int nxfx_pc_setup_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
+  if (!ctx || !r) return NXFX_ERR_INVALID;
+  int rc = dist_ready(ctx, buf);
+  if (rc) return rc;
+  NXFX_REQUIRE(ctx, ctx->assembled, "assemble the matrix before pc_setup");
+  const int nt = std::max(ctx->tree.n_top, 1);
+  if (ctx->N != 1) {
+    if ((rc = nxfx_pc_setup_begin(ctx, buf))) return rc;
+    return nxfx_pc_apply_begin(ctx, r, buf + 2 * (size_t)nt);
+  }
+  NXFX_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(r) & 15) == 0, "vectors must be 16-byte aligned");
+  auto& s = ctx->tree;
+  TreeDev t = make_tree(ctx);
+  const int nb = s.n_chunks - 1;
+  FusedN1 fin{make_net(ctx), r, ctx->cell_rh.p, ctx->lam_weight.p};
+  const size_t smem = tree_smem_bytes_fs(s.cap);
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_factor_solve_bottom_kernel, nb, kTreeThreads, smem, t, fin);
+  NXFX_LAUNCH(ctx, tree_top_fs_kernel<kPartial>, 1, kTreeThreads, smem, t, nb, buf, fin);
+  ctx->bottom_factored = true;
+  return NXFX_OK;
+}
+
+int nxfx_pc_setup_apply_end(nxfx_ctx* ctx, const double* r, double* z, double* buf) {
+  if (!ctx || !r || !z) return NXFX_ERR_INVALID;
+  int rc = dist_ready(ctx, buf);
+  if (rc) return rc;
+  const int nt = std::max(ctx->tree.n_top, 1);
+  if (ctx->N != 1) {
+    if ((rc = nxfx_pc_setup_end(ctx, buf))) return rc;
+    return nxfx_pc_apply_end(ctx, r, z, buf + 2 * (size_t)nt, 0);
+  }
+  NXFX_REQUIRE(ctx, ctx->bottom_factored, "nxfx_pc_setup_apply_begin has not been run");
+  auto& s = ctx->tree;
+  Net g = make_net(ctx);
+  TreeDev t = make_tree(ctx);
+  const int nb = s.n_chunks - 1;
+  FusedN1 fin{g, r, ctx->cell_rh.p, ctx->lam_weight.p};
+  NXFX_LAUNCH(ctx, tree_top_fs_kernel<kFinish>, 1, kTreeThreads, tree_smem_bytes_fs(s.cap), t, nb, buf, fin);
+  ctx->pc_ready = true;
+  if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, tree_smem_bytes(s.cap), t, nb, ctx->ticket.p + 1, 0);
+  const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
+  NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+  return NXFX_OK;
+}
+
 int nxfx_pack_shared(nxfx_ctx* ctx, const double* v, double* buf) {
   if (!ctx || !v || !buf) return NXFX_ERR_INVALID;
   if (ctx->n_shared > 0)
@@ -1167,8 +1219,16 @@ int nxfx_unpack_shared(nxfx_ctx* ctx, const double* buf, double* v) {
 int nxfx_residual_partial(nxfx_ctx* ctx, const double* b, const double* x, double* r, double* buf) {
   if (!ctx || !b || !x || !r || !buf) return NXFX_ERR_INVALID;
   NXFX_REQUIRE(ctx, ctx->has_pattern && ctx->lam_nonshared.p, "nxfx_set_shared has not been called");
-  int rc = do_residual(ctx, b, x, r, slot(ctx, 0));
-  if (rc) return rc;
+  int rc;
+  if (ctx->pipe_ok) {  // the weighted partial norms come out of the residual kernel itself
+    const int ntiles = (int)cdiv(ctx->ndofs, kTileRows);
+    const int grid = std::min(ntiles, ctx->sm_count * kPipeBlocksPerSM);
+    NXFX_LAUNCH(ctx, spmv_pipe_kernel<2>, grid, kTileRows, kPipeSmem, (int)ctx->ndofs, ntiles, ctx->rowptr.p,
+                ctx->colidx.p, ctx->vals.p, ctx->tile_base.p, x, r, b, ctx->scal.p, ctx->ticket.p,
+                buf + ctx->n_shared, (int)ctx->loff, ctx->lam_nonshared.p, ctx->lam_weight.p);
+    return nxfx_pack_shared(ctx, r, buf);
+  }
+  if ((rc = do_residual(ctx, b, x, r, slot(ctx, 0)))) return rc;
   if ((rc = nxfx_pack_shared(ctx, r, buf))) return rc;
   const int n = (int)ctx->ndofs;
   NXFX_LAUNCH(ctx, weighted_norm2_pair_kernel, vec_grid(ctx, n), kThreads, 0, n, (int)ctx->loff, r, ctx->lam_nonshared.p,

@@ -50,12 +50,14 @@ struct FusedN1 {
   Net g;
   const double* r;
   const double* cell_rh;
+  const double* lam_weight = nullptr;  // multi-GPU: weight of this rank's copy of a multiplier row
 };
 
 // n = node in schedule order; its incidences come from the schedule-ordered table (two dependent
 // loads instead of the five of bif_of_t -> bif_ptr -> bif_inc -> edge_slot -> r)
 __device__ __forceinline__ double n1_node_rhs(const FusedN1& f, const TreeDev& t, int n) {
-  double s = -f.r[f.g.loff + t.bif_of_t[n]];
+  const int bi = t.bif_of_t[n];
+  double s = f.lam_weight ? -f.lam_weight[bi] * f.r[f.g.loff + bi] : -f.r[f.g.loff + bi];
   for (int k = t.t_inc_ptr[n]; k < t.t_inc_ptr[n + 1]; ++k) {
     const int2 inc = t.t_inc[k];
     const double2 rq = *reinterpret_cast<const double2*>(f.r + (inc.x & ~1));
@@ -611,6 +613,81 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
     __syncthreads();
   }
   solve_down(t, S, ci);
+}
+
+// Multi-GPU form of the fused factor + first solve: bottom chunks only (no top chunk, no backward
+// sweep) ...
+__global__ void __launch_bounds__(kTreeThreads, 2)
+tree_factor_solve_bottom_kernel(TreeDev t, FusedN1 fin) {
+  extern __shared__ __align__(16) unsigned char tree_smem_raw[];
+  TreeSmem S = tree_view(tree_smem_raw, t.cap);
+  double* Se = reinterpret_cast<double*>(tree_smem_raw + ((tree_smem_bytes(t.cap) + 15) & ~(size_t)15));
+  const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
+  load_children(t, ci, S);
+  factor_solve_up(t, S, Se, ci, false, fin);
+  for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x) t.r[ci.b0 + i] = S.a[i];
+}
+
+// ... and the replicated top chunk in two phases around the caller's SUM all-reduce of
+// buf = [partial d | tg | partial rhs] (3 nn doubles): kPartial folds in this rank's bottom-chunk
+// children, kFinish factorises, eliminates and back-substitutes from the reduced values.
+template <int PHASE>
+__global__ void __launch_bounds__(kTreeThreads)
+tree_top_fs_kernel(TreeDev t, int top_chunk, double* buf, FusedN1 fin) {
+  extern __shared__ __align__(16) unsigned char tree_smem_raw[];
+  TreeSmem S = tree_view(tree_smem_raw, t.cap);
+  double* Se = reinterpret_cast<double*>(tree_smem_raw + ((tree_smem_bytes(t.cap) + 15) & ~(size_t)15));
+  const ChunkInfo ci = load_chunk_info(t, top_chunk, S);
+  const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
+  load_children(t, ci, S);
+  if (PHASE == kPartial) {
+    for (int i = tid; i < nn; i += nth) {
+      const int pe = t.t_pedge[b0 + i];
+      S.a[i] = n1_node_rhs(fin, t, b0 + i);
+      S.b[i] = n1_node_diag(fin, t, b0 + i);
+      Se[i] = pe >= 0 ? 1.0 / fin.cell_rh[pe] : 0.0;
+    }
+    __syncthreads();
+    for (int i = tid; i < nn; i += nth) {
+      double ad = S.b[i], ar = S.a[i];
+      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+        const int c = S.cidx[k];
+        if (c < b0) {
+          ad -= t.tg[c] * t.gd[c];
+          ar += t.gd[c] * t.r[c];
+        }
+      }
+      buf[i] = ad;
+      buf[nn + i] = Se[i];
+      buf[2 * nn + i] = ar;
+    }
+  } else {
+  for (int i = tid; i < nn; i += nth) {
+    S.b[i] = buf[i];
+    Se[i] = buf[nn + i];
+    S.a[i] = buf[2 * nn + i];
+    S.par[i] = t.t_parent[b0 + i];
+    t.tg[b0 + i] = Se[i];  // all-reduced link conductances
+  }
+  __syncthreads();
+  sweep_up(S, ci, [&](int n) {
+    const int i = n - b0;
+    double ad = S.b[i], ar = S.a[i];
+    for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+      const int c = S.cidx[k] - b0;
+      if (c >= 0) {
+        ad -= Se[c] * S.c[c];
+        ar += S.c[c] * S.a[c];
+      }
+    }
+    const double inv = 1.0 / ad;
+    S.b[i] = inv;
+    S.c[i] = Se[i] * inv;
+    S.a[i] = ar;
+  });
+  for (int i = tid; i < nn; i += nth) { t.d[b0 + i] = S.b[i]; t.gd[b0 + i] = S.c[i]; }
+  solve_down(t, S, ci);
+  }
 }
 
 // Edge condensation: c_e = sum r_q - w.F,  F_N = sum r_p

@@ -67,6 +67,7 @@ __device__ __forceinline__ void finish_partials(double (&mine)[K], double* parti
 }
 
 // MODE 0: y = A x.   MODE 1: y = b - A x and norm2_out[0] = ||y||^2, norm2_out[1] = ||b||^2
+// MODE 2 (pipeline kernel): as 1 with the rows >= loff weighted by w_r / w_b (multi-GPU partial norms)
 // (block partials, grid-strided tiles so that the partial count stays bounded).
 template <int MODE>
 __global__ void __launch_bounds__(kTileRows)
@@ -204,7 +205,8 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
                  const int32_t* __restrict__ colidx, const double* __restrict__ vals,
                  const int32_t* __restrict__ tile_base, const double* __restrict__ x,
                  double* __restrict__ y, const double* __restrict__ b, double* partial,
-                 unsigned int* ticket, double* norm2_out) {
+                 unsigned int* ticket, double* norm2_out, int loff = 0,
+                 const double* __restrict__ w_r = nullptr, const double* __restrict__ w_b = nullptr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SpmvStage* st = reinterpret_cast<SpmvStage*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(SpmvStage));
@@ -252,7 +254,7 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
     const int r0 = tile * kTileRows;
     const int nr = min(kTileRows, n - r0);
     double bi = 0.0;
-    if (MODE == 1 && tid < nr) bi = __ldcs(b + r0 + tid);
+    if (MODE >= 1 && tid < nr) bi = __ldcs(b + r0 + tid);
     mbar_wait(full + s, (uint32_t)((it / kStages) & 1));
     SpmvStage& S = st[s];
     const int base = S.rows[0];
@@ -286,15 +288,20 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
       } else {
         const double r = __dsub_rn(bi, acc);
         y[r0 + tid] = r;
-        nrm += r * r;
-        nrb += bi * bi;
+        if (MODE == 2 && r0 + tid >= loff) {  // multi-GPU: weighted multiplier rows
+          nrm += w_r[r0 + tid - loff] * r * r;
+          nrb += w_b[r0 + tid - loff] * bi * bi;
+        } else {
+          nrm += r * r;
+          nrb += bi * bi;
+        }
       }
     }
     // order this thread's generic-proxy accesses to the stage before the TMA refill
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
   }
-  if (MODE == 1) {
+  if (MODE >= 1) {
     double mine[2] = {block_sum<kTileRows>(nrm, red), block_sum<kTileRows>(nrb, red)};
     finish_partials<kTileRows, 2>(mine, partial, gridDim.x, ticket, norm2_out, red);
   }

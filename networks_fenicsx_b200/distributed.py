@@ -192,13 +192,10 @@ class DistributedSolver:
         x = self.solver.x.device_ptr_overwrite()
         # factorisation and first application share one all-reduce: the forward sweep of the bottom
         # chunks only needs their own factors
-        nt = max(self.part.n_top, 1)
-        top, top_rhs = self._ptr(self._top), self._ptr(self._top, 2 * nt)
-        dev.call("nxfx_pc_setup_begin", top)
-        dev.call("nxfx_pc_apply_begin", b, top_rhs)
+        top = self._ptr(self._top)  # [partial pivots | link conductances | partial rhs], 3 n_top
+        dev.call("nxfx_pc_setup_apply_begin", b, top)
         self._dist.all_reduce(self._top, group=self._group)
-        dev.call("nxfx_pc_setup_end", top)
-        dev.call("nxfx_pc_apply_end", b, x, top_rhs, 0)
+        dev.call("nxfx_pc_setup_apply_end", b, x, top)
         self.history = []
         applied = 0
         while refine_steps > 0 or final_residual:
