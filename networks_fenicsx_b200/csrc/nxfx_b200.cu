@@ -126,9 +126,23 @@ int do_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, doub
   const int ntiles = (int)cdiv(ctx->ndofs, kTileRows);
   if (ctx->pipe_ok) {
     const int grid = std::min(ntiles, ctx->sm_count * kPipeBlocksPerSM);
-    NXFX_LAUNCH(ctx, spmv_pipe_kernel<1>, grid, kTileRows, kPipeSmem, (int)ctx->ndofs, ntiles,
-                ctx->rowptr.p, ctx->colidx.p, ctx->vals.p, ctx->tile_base.p, x, r, b, ctx->scal.p,
-                ctx->ticket.p, norm2_d);
+    // programmatic dependent launch: the blocks set up their pipeline and prefetch matrix tiles
+    // while the preceding kernel (normally the back-substitution producing x) drains
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTileRows);
+    cfg.dynamicSmemBytes = kPipeSmem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NXFX_CUDA(ctx, cudaLaunchKernelEx(&cfg, spmv_pipe_kernel<1>, (int)ctx->ndofs, ntiles, (const int32_t*)ctx->rowptr.p,
+                                      (const int32_t*)ctx->colidx.p, (const double*)ctx->vals.p,
+                                      (const int32_t*)ctx->tile_base.p, x, r, b, ctx->scal.p, ctx->ticket.p, norm2_d, 0,
+                                      (const double*)nullptr, (const double*)nullptr));
+    ctx->launches++;
     return NXFX_OK;
   }
   const int grid = std::min(ntiles, kMaxPartials);

@@ -737,6 +737,9 @@ __global__ void __launch_bounds__(kThreads)
 edge_backsub_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh,
                     const double* __restrict__ r, const double* __restrict__ edge_g,
                     const double* __restrict__ edge_c, double* __restrict__ z) {
+  // let a dependent residual kernel (launched with programmatic stream serialisation) move in and
+  // prefetch its first matrix tiles while this grid drains
+  asm volatile("griddepcontrol.launch_dependents;");
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= g.E) {
     const int i = idx - g.E;
@@ -808,6 +811,9 @@ template <bool ADD>
 __global__ void __launch_bounds__(kThreads)
 edge_backsub_n1_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh, const double* __restrict__ r,
                        double* __restrict__ z) {
+  // let a dependent residual kernel (launched with programmatic stream serialisation) move in and
+  // prefetch its first matrix tiles while this grid drains
+  asm volatile("griddepcontrol.launch_dependents;");
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= g.E) {
     const int i = idx - g.E;

@@ -239,6 +239,10 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
       if (tile < ntiles) issue(tile, k);
     }
   }
+  // Programmatic dependent launch: everything above only touches the matrix (complete long before
+  // the preceding kernel started); x, b, y and the reduction scratch are used below.  A no-op when
+  // the kernel was launched without the attribute.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   double nrm = 0.0, nrb = 0.0;
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
