@@ -515,6 +515,9 @@ __global__ void __launch_bounds__(kTileRows)
 assemble_tiles_kernel(Net g, Coef c, const int32_t* __restrict__ rowptr, double* __restrict__ vals,
                       double* __restrict__ b, int lhs, int rhs, int n_flux_tiles, int n_pres_tiles) {
   __shared__ __align__(16) double sm[kAsmCap + 2];
+  // a kernel launched as programmatic dependent (the fused tree kernel) may stage its schedule
+  // tables while the last wave of this grid drains; it waits for this grid before reading any output
+  asm volatile("griddepcontrol.launch_dependents;");
   // flux tiles first, then pressure, then multiplier tiles: each region is written as one
   // ascending stream (interleaving the tile types along the block index measured 6 % slower)
   const int t = blockIdx.x;

@@ -88,6 +88,7 @@ struct nxfx_ctx {
   nxfx::DevBuf<unsigned int> ticket;  // [0] reductions, [1] tree sweeps, [2] tree epoch flag
   double* scal_h = nullptr;  // pinned mirror (mapped: kernels may store results into it)
   double* scal_h_dev = nullptr;  // its device address
+  bool pdl_coop_refused = false;  // the driver refused cooperative + programmatic launch
   // multi-GPU: replicated multipliers
   int32_t n_shared = 0;
   nxfx::DevBuf<int32_t> shared_lm;

@@ -122,8 +122,17 @@ int do_spmv(nxfx_ctx* ctx, const double* x, double* y) {
   return NXFX_OK;
 }
 
-int do_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, double* norm2_d) {
+// pdl: launch as programmatic dependent of the preceding kernel -- only where that kernel does not
+// write the matrix (the blocks prefetch matrix tiles before they wait for it)
+int do_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, double* norm2_d, bool pdl = false) {
   const int ntiles = (int)cdiv(ctx->ndofs, kTileRows);
+  if (ctx->pipe_ok && !pdl) {
+    const int grid = std::min(ntiles, ctx->sm_count * kPipeBlocksPerSM);
+    NXFX_LAUNCH(ctx, spmv_pipe_kernel<1>, grid, kTileRows, kPipeSmem, (int)ctx->ndofs, ntiles,
+                ctx->rowptr.p, ctx->colidx.p, ctx->vals.p, ctx->tile_base.p, x, r, b, ctx->scal.p,
+                ctx->ticket.p, norm2_d);
+    return NXFX_OK;
+  }
   if (ctx->pipe_ok) {
     const int grid = std::min(ntiles, ctx->sm_count * kPipeBlocksPerSM);
     // programmatic dependent launch: the blocks set up their pipeline and prefetch matrix tiles
@@ -288,13 +297,39 @@ int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z) {
   unsigned int* fl = ctx->ticket.p + 2;
   unsigned int ep = ++s.epoch;
   int nb = s.n_chunks - 1;
-  void* args[] = {&t, &nb, &tk, &fl, &ep, &fin};
-  NXFX_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tree_factor_solve_coop_kernel), dim3(nb),
-                                             dim3(kTreeThreads), args, tree_smem_bytes_fs(s.cap), ctx->stream));
+  // both kernels are programmatic dependents of their predecessor: the tree kernel stages its
+  // schedule tables while the assembly drains, the back-substitution its edge data while the tree
+  // kernel finishes (cooperative + programmatic launch; plain cooperative launch if refused)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nb);
+  cfg.blockDim = dim3(kTreeThreads);
+  cfg.dynamicSmemBytes = tree_smem_bytes_fs(s.cap);
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx->pdl_coop_refused ? 1 : 2;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, tree_factor_solve_coop_kernel, t, nb, tk, fl, ep, fin);
+  if (le != cudaSuccess && cfg.numAttrs == 2) {
+    cudaGetLastError();
+    ctx->pdl_coop_refused = true;
+    cfg.numAttrs = 1;
+    le = cudaLaunchKernelEx(&cfg, tree_factor_solve_coop_kernel, t, nb, tk, fl, ep, fin);
+  }
+  NXFX_CUDA(ctx, le);
   ctx->launches++;
   ctx->pc_ready = true;
-  const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
-  NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+  cudaLaunchConfig_t bc = {};
+  bc.gridDim = dim3((unsigned)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads));
+  bc.blockDim = dim3(kThreads);
+  bc.stream = ctx->stream;
+  bc.attrs = attr + 1;
+  bc.numAttrs = 1;
+  NXFX_CUDA(ctx, cudaLaunchKernelEx(&bc, edge_backsub_n1_kernel<false>, g, t, (const double*)ctx->cell_rh.p, r, z));
+  ctx->launches++;
   return NXFX_OK;
 }
 
@@ -393,7 +428,7 @@ int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_op
   int applied = 0;
   while (true) {
     // the reducing block stores the two norms straight into mapped pinned memory: no copy-engine hop
-    if ((rc = do_residual(ctx, b, x, r, ctx->scal_h_dev))) return rc;
+    if ((rc = do_residual(ctx, b, x, r, ctx->scal_h_dev, true))) return rc;
     NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     info->rhs_norm = std::sqrt(ctx->scal_h[1]);
     info->residual_norm = std::sqrt(ctx->scal_h[0]);

@@ -586,6 +586,11 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
   double* Se = reinterpret_cast<double*>(tree_smem_raw + ((tree_smem_bytes(t.cap) + 15) & ~(size_t)15));
   const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
   load_children(t, ci, S);
+  // programmatic dependent launch: the schedule tables above are static; everything below reads the
+  // output of the preceding kernels.  Dependents (the back-substitution) are released only now, so
+  // that whatever they read before their own wait is complete as well.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
   factor_solve_up(t, S, Se, ci, false, fin);
   // the eliminated right-hand side of the whole chunk goes to HBM: later solves reuse the factors,
   // the top chunk reads the roots, and the last block recycles its staging buffer
@@ -816,17 +821,21 @@ edge_backsub_n1_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh, con
   asm volatile("griddepcontrol.launch_dependents;");
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= g.E) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int i = idx - g.E;
     if (i < g.n_bif) { if (ADD) z[g.loff + i] += t.lam_nat[i]; else z[g.loff + i] = t.lam_nat[i]; }
     return;
   }
+  // as a programmatic dependent of the tree kernel: r and cell_rh are older than that kernel
+  // (it releases its dependents only after its own wait), the multipliers are its output
   const int e = idx;
   const int slot = g.edge_slot[e];
   const int4 uv = g.slot_uvl[slot];
-  const double lu = uv.z >= 0 ? t.lam_nat[uv.z] : 0.0;
-  const double lv = uv.w >= 0 ? t.lam_nat[uv.w] : 0.0;
   const double2 rq = *reinterpret_cast<const double2*>(r + 2 * (size_t)slot);
   const double rp = r[g.poff + e], rh = cell_rh[e];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const double lu = uv.z >= 0 ? t.lam_nat[uv.z] : 0.0;
+  const double lv = uv.w >= 0 ? t.lam_nat[uv.w] : 0.0;
   const double c = (rq.x + rq.y) - 0.5 * rh * rp;
   const double q0 = (c + lu - lv) / rh;
   const double q1 = q0 + rp;
