@@ -301,7 +301,7 @@ int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z) {
   // schedule tables while the assembly drains, the back-substitution its edge data while the tree
   // kernel finishes (cooperative + programmatic launch; plain cooperative launch if refused)
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nb);
+  cfg.gridDim = dim3(nb + 1);  // the last block owns the top chunk
   cfg.blockDim = dim3(kTreeThreads);
   cfg.dynamicSmemBytes = tree_smem_bytes_fs(s.cap);
   cfg.stream = ctx->stream;
@@ -918,7 +918,7 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
                                           (int)tree_smem_bytes_fs(kChunkCapMax)) == cudaSuccess &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_factor_solve_coop_kernel, kTreeThreads,
                                                       tree_smem_bytes_fs(ctx->tree.cap)) == cudaSuccess)
-      s.coop_fs_ok = (n_chunks - 1) <= per_sm * ctx->sm_count;
+      s.coop_fs_ok = n_chunks <= per_sm * ctx->sm_count;  // bottom blocks + one block for the top chunk
     cudaGetLastError();
     NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));
     NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<true, kPartial>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));

@@ -531,8 +531,11 @@ __host__ __device__ constexpr size_t tree_smem_bytes_fs(int cap) {
   return ((tree_smem_bytes(cap) + 15) & ~(size_t)15) + (size_t)cap * sizeof(double);
 }
 
+// wait_ticket (top chunk in its own block): the chunk's own values are staged first, then the block
+// waits until all wait_count bottom blocks have published their roots.
 __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem& S, double* __restrict__ Se,
-                                                const ChunkInfo& ci, bool top, const FusedN1& f) {
+                                                const ChunkInfo& ci, bool top, const FusedN1& f,
+                                                unsigned int* wait_ticket = nullptr, int wait_count = 0) {
   const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
   for (int i = tid; i < nn; i += nth) {
     S.a[i] = n1_node_rhs(f, t, b0 + i);
@@ -545,6 +548,13 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
   }
   __syncthreads();
   if (top) {  // fold in the bottom-chunk children (written by the other blocks of this launch)
+    if (wait_ticket) {
+      if (tid == 0) {
+        while (atomicAdd(wait_ticket, 0u) != (unsigned int)wait_count) __nanosleep(32);
+        __threadfence();
+      }
+      __syncthreads();
+    }
     for (int i = tid; i < nn; i += nth) {
       double ad = S.b[i], ar = S.a[i];
       for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
@@ -578,6 +588,10 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
   for (int i = tid; i < nn; i += nth) { t.d[b0 + i] = S.b[i]; t.gd[b0 + i] = S.c[i]; }
 }
 
+// grid = n_bottom + 1 co-resident blocks (cooperative launch).  The LAST block owns the top chunk: it
+// stages the chunk's own diagonals / right-hand sides while the bottom blocks work, waits for their
+// roots (ticket), factorises + solves the top chunk and raises the epoch flag; the bottom blocks
+// then back-substitute their chunk straight from shared memory.
 __global__ void __launch_bounds__(kTreeThreads, 2)
 tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch,
                               FusedN1 fin) {
@@ -591,15 +605,9 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
   // that whatever they read before their own wait is complete as well.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;");
-  factor_solve_up(t, S, Se, ci, false, fin);
-  // the eliminated right-hand side of the whole chunk goes to HBM: later solves reuse the factors,
-  // the top chunk reads the roots, and the last block recycles its staging buffer
-  for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x) t.r[ci.b0 + i] = S.a[i];
-  if (last_block_done(S, ticket, n_bottom)) {
-    const ChunkInfo ti = load_chunk_info(t, n_bottom, S);
-    load_children(t, ti, S);
-    factor_solve_up(t, S, Se, ti, true, fin);
-    solve_down(t, S, ti);
+  if ((int)blockIdx.x == n_bottom) {
+    factor_solve_up(t, S, Se, ci, true, fin, ticket, n_bottom);
+    solve_down(t, S, ci);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -607,16 +615,20 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
       __threadfence();
       atomicExch(flag, epoch);
     }
-    load_chunk_info(t, blockIdx.x, S);
-    load_solve_chunk(t, ci, S);
-    __syncthreads();
-  } else {
-    if (threadIdx.x == 0) {
-      while (atomicAdd(flag, 0u) != epoch) __nanosleep(64);
-      __threadfence();
-    }
-    __syncthreads();
+    return;
   }
+  factor_solve_up(t, S, Se, ci, false, fin);
+  // publish the eliminated right-hand sides of the chunk roots for the top chunk
+  for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x)
+    if (S.par[i] < ci.b0 || S.par[i] >= ci.b1) t.r[ci.b0 + i] = S.a[i];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(ticket, 1u);
+    while (atomicAdd(flag, 0u) != epoch) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
   solve_down(t, S, ci);
 }
 
