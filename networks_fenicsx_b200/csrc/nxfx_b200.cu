@@ -240,7 +240,7 @@ int tree_pass(nxfx_ctx* ctx, bool factor, const double* fuse_r = nullptr, bool f
       unsigned int ep = ++s.epoch;
       int nbv = nb;
       void* args[] = {&t, &nbv, &tk, &fl, &ep, &fin};
-      NXFX_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tree_solve_coop_kernel), dim3(nb), dim3(kTreeThreads),
+      NXFX_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tree_solve_coop_kernel), dim3(nb + 1), dim3(kTreeThreads),
                                                  args, tree_smem_bytes(ctx->tree.cap), ctx->stream));
       ctx->launches++;
     } else {
@@ -907,7 +907,7 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
     if (coop && cudaFuncSetAttribute(tree_solve_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)tree_smem_bytes(kChunkCapMax)) == cudaSuccess &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_solve_coop_kernel, kTreeThreads, tree_smem_bytes(ctx->tree.cap)) == cudaSuccess)
-      s.coop_ok = (n_chunks - 1) <= per_sm * ctx->sm_count;
+      s.coop_ok = n_chunks <= per_sm * ctx->sm_count;  // bottom blocks + one block for the top chunk
     cudaGetLastError();
     NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_factor_solve_bottom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes_fs(kChunkCapMax)));
     NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_top_fs_kernel<kPartial>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes_fs(kChunkCapMax)));

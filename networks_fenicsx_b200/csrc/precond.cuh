@@ -68,6 +68,23 @@ __device__ __forceinline__ double n1_node_rhs(const FusedN1& f, const TreeDev& t
   return s;
 }
 
+// both at once (one pass over the incidences; same operations in the same order as the two above)
+__device__ __forceinline__ double n1_node_rhs_diag(const FusedN1& f, const TreeDev& t, int n, double& diag) {
+  const int bi = t.bif_of_t[n];
+  double s = f.lam_weight ? -f.lam_weight[bi] * f.r[f.g.loff + bi] : -f.r[f.g.loff + bi];
+  double d = 0.0;
+  for (int k = t.t_inc_ptr[n]; k < t.t_inc_ptr[n + 1]; ++k) {
+    const int2 inc = t.t_inc[k];
+    const double2 rq = *reinterpret_cast<const double2*>(f.r + (inc.x & ~1));
+    const double rp = f.r[f.g.poff + inc.y], rh = f.cell_rh[inc.y];
+    const double gc = ((rq.x + rq.y) - 0.5 * rh * rp) / rh;
+    s += (inc.x & 1) ? (rp + gc) : -gc;
+    d += 1.0 / rh;
+  }
+  diag = d;
+  return s;
+}
+
 __device__ __forceinline__ double n1_node_diag(const FusedN1& f, const TreeDev& t, int n) {
   double s = 0.0;
   for (int k = t.t_inc_ptr[n]; k < t.t_inc_ptr[n + 1]; ++k) s += 1.0 / f.cell_rh[t.t_inc[k].y];
@@ -475,8 +492,10 @@ tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top) {
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
-// single-launch solve: requires all n_bottom blocks to be co-resident (cooperative launch); two
-// blocks per SM (<= 32 registers) so that 20 generations (256 bottom chunks) fit 148 SMs
+// single-launch solve: grid = n_bottom + 1 co-resident blocks (cooperative launch; two blocks per
+// SM, <= 32 registers, so that 20 generations fit 148 SMs).  The last block owns the top chunk: it
+// stages it while the bottom blocks sweep, waits for their roots (ticket), solves the top chunk and
+// raises the epoch flag; the bottom blocks then back-substitute straight from shared memory.
 __global__ void __launch_bounds__(kTreeThreads, 2)
 tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch,
                        FusedN1 fin) {
@@ -487,21 +506,14 @@ tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned i
   load_children(t, ci, S);
   load_solve_chunk(t, ci, S, f);
   __syncthreads();
-  solve_up(t, S, ci, false);
-  // publish the chunk roots (the shallowest levels may hold several subtree roots: publish the
-  // whole chunk only in the block that will recycle its staging buffer)
-  for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x)
-    if (S.par[i] < ci.b0 || S.par[i] >= ci.b1) t.r[ci.b0 + i] = S.a[i];
-  if (last_block_done(S, ticket, n_bottom)) {
-    // park this block's chunk, solve the top chunk in the same buffer, reload
-    for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x) t.r[ci.b0 + i] = S.a[i];
+  if ((int)blockIdx.x == n_bottom) {
+    if (threadIdx.x == 0) {
+      while (atomicAdd(ticket, 0u) != (unsigned int)n_bottom) __nanosleep(32);
+      __threadfence();
+    }
     __syncthreads();
-    const ChunkInfo ti = load_chunk_info(t, n_bottom, S);
-    load_children(t, ti, S);
-    load_solve_chunk(t, ti, S, f);
-    __syncthreads();
-    solve_up(t, S, ti, true);
-    solve_down(t, S, ti);
+    solve_up(t, S, ci, true);
+    solve_down(t, S, ci);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -509,16 +521,19 @@ tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned i
       __threadfence();
       atomicExch(flag, epoch);
     }
-    load_chunk_info(t, blockIdx.x, S);
-    load_solve_chunk(t, ci, S);
-    __syncthreads();
-  } else {
-    if (threadIdx.x == 0) {
-      while (atomicAdd(flag, 0u) != epoch) __nanosleep(64);
-      __threadfence();
-    }
-    __syncthreads();
+    return;
   }
+  solve_up(t, S, ci, false);
+  for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x)
+    if (S.par[i] < ci.b0 || S.par[i] >= ci.b1) t.r[ci.b0 + i] = S.a[i];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(ticket, 1u);
+    while (atomicAdd(flag, 0u) != epoch) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
   solve_down(t, S, ci);
 }
 
@@ -538,8 +553,9 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
                                                 unsigned int* wait_ticket = nullptr, int wait_count = 0) {
   const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
   for (int i = tid; i < nn; i += nth) {
-    S.a[i] = n1_node_rhs(f, t, b0 + i);
-    S.b[i] = n1_node_diag(f, t, b0 + i);
+    double dg;
+    S.a[i] = n1_node_rhs_diag(f, t, b0 + i, dg);
+    S.b[i] = dg;
     const int pe = t.t_pedge[b0 + i];
     const double tg = pe >= 0 ? 1.0 / f.cell_rh[pe] : 0.0;
     Se[i] = tg;
