@@ -428,13 +428,17 @@ int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_op
   int applied = 0;
   while (true) {
     // the reducing block stores the two norms straight into mapped pinned memory: no copy-engine hop
-    if ((rc = do_residual(ctx, b, x, r, ctx->scal_h_dev, true))) return rc;
+    // Only the norms are needed for the decision: the residual vector itself is written (by a second
+    // pass, bit-identical) only if a correction follows -- never on trees.
+    const bool lazy = ctx->pipe_ok;
+    if ((rc = do_residual(ctx, b, x, lazy ? nullptr : r, ctx->scal_h_dev, true))) return rc;
     NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     info->rhs_norm = std::sqrt(ctx->scal_h[1]);
     info->residual_norm = std::sqrt(ctx->scal_h[0]);
     push_history(info, info->residual_norm);
     const bool good = std::isfinite(info->residual_norm) && info->residual_norm <= rt * info->rhs_norm;
     if (applied >= steps || (good && rt > 0.0) || !std::isfinite(info->residual_norm)) break;
+    if (lazy && (rc = do_residual(ctx, b, x, r, slot(ctx, 0)))) return rc;
     if ((rc = do_pc_apply(ctx, o->pc_type, r, x, true))) return rc;
     ++applied;
     if (applied >= steps && !o->final_residual) break;  // residual of the iterate before the last correction

@@ -291,7 +291,7 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
         y[r0 + tid] = acc;
       } else {
         const double r = __dsub_rn(bi, acc);
-        y[r0 + tid] = r;
+        if (y) y[r0 + tid] = r;  // y == nullptr: norms only
         if (MODE == 2 && r0 + tid >= loff) {  // multi-GPU: weighted multiplier rows
           nrm += w_r[r0 + tid - loff] * r * r;
           nrb += w_b[r0 + tid - loff] * bi * bi;
