@@ -1,6 +1,6 @@
 """Multi-GPU check of the single-tree partition (run under torchrun on >= 2 GPUs):
 
-    torchrun --nproc-per-node 2 scripts/dist_check.py [generations] [N]
+    torchrun --nproc-per-node 2 tests/dist_check.py [generations] [N]
 
 Every rank solves its part; rank 0 gathers the solution and compares it with the CPU oracle's
 direct solve of the WHOLE network (bar: 1e-8 relative L2, BASELINE north_star)."""

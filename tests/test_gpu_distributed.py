@@ -1,5 +1,5 @@
 """Multi-GPU parity: one tree cut over 2 GPUs, gathered solution vs the oracle's direct solve of
-the whole network (scripts/dist_check.py under torchrun).  Skipped on single-GPU boxes."""
+the whole network (tests/dist_check.py under torchrun).  Skipped on single-GPU boxes."""
 
 import pathlib
 import subprocess
@@ -18,7 +18,7 @@ def test_single_tree_partition_two_gpus(args):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29631", str(ROOT / "scripts" / "dist_check.py"), *args]
+           "--master-addr", "127.0.0.1", "--master-port", "29631", str(ROOT / "tests" / "dist_check.py"), *args]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "-> OK" in out.stdout
