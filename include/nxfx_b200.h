@@ -100,7 +100,21 @@ int nxfx_mesh_geometry_device(nxfx_ctx* ctx, const double** x_d); /* [n_vertices
  * explicit zeros DOLFINx stores in the multiplier blocks.                                         */
 int nxfx_symbolic(nxfx_ctx* ctx);
 int nxfx_csr_device(nxfx_ctx* ctx, const int32_t** rowptr_d, const int32_t** colidx_d,
-                    double** values_d);
+                    double** values_d); /* values of the BOUND matrix */
+
+/* Matrices on the ctx's pattern.  The reference hands out independent PETSc Mats: Solver.__init__
+ * (solver.py:43) creates one, every assembler.assemble() without A creates another
+ * (assembly.py:354).  A matrix owns its CSR values and the per-cell R*h the network-Schur
+ * factorisation is built from; it records how many assemblies were accumulated into it
+ * (ADD_VALUES without zeroEntries).  The BOUND matrix is the target of nxfx_assemble and the
+ * operator of nxfx_spmv / nxfx_residual / nxfx_pc_* / nxfx_solve.  The symbolic phase creates and
+ * binds matrix 0; a new pattern (nxfx_symbolic / nxfx_set_generic_system / nxfx_set_network)
+ * destroys every matrix of the old one.  Binding another matrix invalidates the factorisation.   */
+int nxfx_matrix_create(nxfx_ctx* ctx, int64_t* mat_id); /* zeroed values */
+int nxfx_matrix_destroy(nxfx_ctx* ctx, int64_t mat_id);
+int nxfx_matrix_bind(nxfx_ctx* ctx, int64_t mat_id);
+int nxfx_matrix_zero(nxfx_ctx* ctx);                    /* MatZeroEntries on the bound matrix */
+int nxfx_matrix_info(nxfx_ctx* ctx, int64_t* mat_id, int32_t* assembled, int32_t* acc_count);
 
 /* ---- (3) numeric assembly ----------------------------------------------------------------- *
  * Replaces fem.petsc.assemble_matrix + A.assemble() + assemble_vector + ghost update:
@@ -113,7 +127,10 @@ int nxfx_csr_device(nxfx_ctx* ctx, const int32_t** rowptr_d, const int32_t** col
  *   accumulate                  0: overwrite (the matrix/vector was zeroed: solver.py:97-100);
  *                               1: add to the existing entries (PETSc ADD_VALUES semantics)
  *   b_d [n_dofs]                right-hand side (written when rhs != 0)
- * Matrix values go to the ctx-owned CSR value array (nxfx_csr_device).                            */
+ * Matrix values go to the bound matrix (nxfx_matrix_bind; default: matrix 0).  The per-cell R*h
+ * that the solver's factorisation uses is written / accumulated together with the values (lhs
+ * only), so the factorisation always belongs to the matrix as it stands: a second accumulated
+ * assembly, or an rhs-only re-assembly with a different R, cannot put the two out of step.        */
 int nxfx_set_boundary_pressure(nxfx_ctx* ctx, const double* pbc_vertex_d);
 int nxfx_assemble(nxfx_ctx* ctx, const double* R_cell_d, double R_const, const double* f_cell_d,
                   double f_const, int lhs, int rhs, int accumulate, double* b_d);

@@ -81,6 +81,13 @@ SIGNATURES = {
     "nxfx_csr_device": (
         C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     ),
+    "nxfx_matrix_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "nxfx_matrix_destroy": (C.c_int, [C.c_void_p, C.c_int64]),
+    "nxfx_matrix_bind": (C.c_int, [C.c_void_p, C.c_int64]),
+    "nxfx_matrix_zero": (C.c_int, [C.c_void_p]),
+    "nxfx_matrix_info": (
+        C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    ),
     "nxfx_set_boundary_pressure": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nxfx_assemble": (
         C.c_int,

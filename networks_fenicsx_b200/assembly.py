@@ -187,6 +187,7 @@ class HydraulicNetworkAssembler:
         self._pbc_d.upload(pbc, sync=False)
         dev.call("nxfx_set_boundary_pressure", self._pbc_d.c_ptr)  # into the vertex records
         dev.sync()
+        nm._pbc_owner = self  # the vertex records now hold THIS assembler's boundary data
         self._R = self._coefficient(R, 1.0, nc, "R")
         self._f = self._coefficient(f, 0.0, nc, "f")
         C_ = nm.num_edge_colors
@@ -281,7 +282,19 @@ class HydraulicNetworkAssembler:
         if self._a is None:
             raise RuntimeError("compute_forms() must be called before creating the matrix")
         dev = self._network_mesh.device
+        nm = self._network_mesh
+        owner = getattr(nm, "_pattern_degrees", None)
+        if owner is not None and owner != self._degrees:
+            # one sparsity pattern per device context: a second assembler with other degrees would
+            # silently replace the pattern under the first one's matrices
+            raise RuntimeError(
+                f"this NetworkMesh already carries the pattern of a flux/pressure degree {owner} assembler; "
+                f"build a second NetworkMesh for degrees {self._degrees}"
+            )
+        if not self._symbolic_done and owner is not None:
+            self._symbolic_done = True  # same degrees: the pattern on the device is the one we need
         if not self._symbolic_done:
+            nm._pattern_degrees = self._degrees
             if self._generic is None:
                 dev.call("nxfx_symbolic")
             else:
@@ -327,12 +340,19 @@ class HydraulicNetworkAssembler:
         if assemble_rhs and b is None:
             b = self.create_vector(kind=kind)
             b.zeroEntries()
+        nm = self._network_mesh
+        if getattr(nm, "_pbc_owner", None) is not self and assemble_rhs:
+            # another assembler on the same network set its boundary data since: restore ours
+            dev.call("nxfx_set_boundary_pressure", self._pbc_d.c_ptr)
+            nm._pbc_owner = self
+        if assemble_lhs:
+            A.bind()
         # zeroed targets are overwritten without being read; otherwise ADD_VALUES semantics
         a_zero = A.consume_zero() if assemble_lhs else True
         b_zero = (b._zero_pending and not b._host_dirty) if assemble_rhs else True
         if assemble_lhs and assemble_rhs and a_zero != b_zero:
             if a_zero:
-                A.values.zero()
+                A.zero_now()
             acc = True
         else:
             acc = not (a_zero if assemble_lhs else b_zero)

@@ -62,7 +62,7 @@ struct Coef {
   const double* __restrict__ R_cell;  // [nc] or null
   const double* __restrict__ f_cell;  // [nc] or null
   double R_const, f_const;
-  double* __restrict__ cell_rh;  // [nc] out
+  double* __restrict__ cell_rh;  // [nc] out: R*h per cell, written with the matrix (lhs); N == 1: indexed by flux SLOT
 };
 
 constexpr double kThird = 1.0 / 3.0;
@@ -233,7 +233,7 @@ struct RowDesc {
 
 template <bool ACC, bool N1, typename Sink>
 __device__ __forceinline__ void assemble_row(const Net& g, const Coef& c, const RowDesc& d, int r, int p,
-                                             int lane, double* __restrict__ b, int rhs, const Sink& put) {
+                                             int lane, double* __restrict__ b, int lhs, int rhs, const Sink& put) {
   const int N = N1 ? 1 : g.N;
   // ---- flux rows: geometry phase (all lanes take part in the shuffles) ----------------------
   const bool isflux = r < g.nq;
@@ -246,7 +246,9 @@ __device__ __forceinline__ void assemble_row(const Net& g, const Coef& c, const 
       const VertexRec v1 = load_vertex(g.x2, N1 ? t.y : vertex_id(g, e, t.x, t.y, a + 1));
       const double R = c.R_cell ? c.R_cell[(size_t)e * N + a] : c.R_const;
       mR = __dmul_rn(R, seg_length(v0, v1));
-      c.cell_rh[(size_t)e * N + a] = mR;
+      if (lhs) {  // the factorisation is built from cell_rh: it must follow the matrix (ADD_VALUES included)
+        if (ACC) c.cell_rh[(size_t)e * N + a] += mR; else c.cell_rh[(size_t)e * N + a] = mR;
+      }
       pA = v0.p;
       pNext = v1.p;
     }
@@ -377,52 +379,74 @@ __device__ __forceinline__ void flush_tile(const double* sm, double* __restrict_
   }
 }
 
-// N == 1 flux tile: thread <-> edge slot, rows 2*slot (vertex u) and 2*slot+1 (vertex v)
+// N == 1 flux tile: thread <-> edge slot, rows 2*slot (vertex u) and 2*slot+1 (vertex v).
+// Everything the thread needs comes from its 16-byte slot record {u, v, lm(u), lm(v)} and the two vertex
+// records: the row's CSR offset inside the tile is 6 * (slots before) + 2 * (multiplier entries before) --
+// a ballot / popcount prefix over the block instead of a strided rowptr load --, and R*h is stored in SLOT
+// order (coalesced; the graph-edge index is only needed for a per-cell R array).
 template <bool ACC>
 __device__ __forceinline__ void flux_tile_n1(const Net& g, const Coef& c, const int32_t* __restrict__ rowptr,
                                              double* __restrict__ vals, double* __restrict__ b, int lhs,
                                              int rhs, int tile, double* sm) {
+  __shared__ int warp_nl[kTileRows / 32];
   const int r0 = tile * kFluxRowsN1;
-  const int rend = min(r0 + kFluxRowsN1, g.nq);
+  const int slot = (r0 >> 1) + threadIdx.x;
+  const bool active = slot < g.E;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int4 t = make_int4(0, 0, -1, -1);
+  if (active) t = NXFX_LDS(g.slot_uvl + slot);
+  const bool hu = t.z >= 0, hv = t.w >= 0;
+  const unsigned bu = __ballot_sync(0xffffffffu, hu), bv = __ballot_sync(0xffffffffu, hv);
+  const unsigned lt = (1u << lane) - 1u;
+  int pre = __popc(bu & lt) + __popc(bv & lt);  // multiplier entry pairs of the earlier lanes
+  if (lane == 0) warp_nl[w] = __popc(bu) + __popc(bv);
   const int sbase = rowptr[r0];
-  const int tnnz = rowptr[rend] - sbase;
-  const int r = r0 + 2 * threadIdx.x;
-  if (r < rend) {
-    const int slot = r >> 1;
-    const int4 t = NXFX_LDS(g.slot_uvl + slot);
-    const int e = NXFX_LDS(g.slot_edge + slot);
-    const int start = NXFX_LDS(rowptr + r) - sbase;
-    const VertexRec v0 = load_vertex(g.x2, t.x), v1 = load_vertex(g.x2, t.y);
-    const double R = c.R_cell ? c.R_cell[e] : c.R_const;
-    const double m = __dmul_rn(R, seg_length(v0, v1));
-    NXFX_ST1(c.cell_rh + e, m);
+  double m = 0.0;
+  VertexRec v0, v1;
+  if (active) {
+    v0 = load_vertex(g.x2, t.x);
+    v1 = load_vertex(g.x2, t.y);
+    const double R = c.R_cell ? c.R_cell[NXFX_LDS(g.slot_edge + slot)] : c.R_const;
+    m = __dmul_rn(R, seg_length(v0, v1));
+  }
+  __syncthreads();
+  int tot = 0;
+#pragma unroll
+  for (int k = 0; k < kTileRows / 32; ++k) {
+    const int v = warp_nl[k];
+    if (k < w) pre += v;
+    tot += v;
+  }
+  const int nact = min(kFluxRowsN1 >> 1, g.E - (r0 >> 1));
+  const int tnnz = 6 * nact + 2 * tot;  // == rowptr[rend] - sbase
+  if (active) {
+    const int r = 2 * slot;
     if (rhs) {
       // assembly.py:258-260: -p_bc at out_marker vertices (boundary START), +p_bc at in_marker (END)
-      const double b0 = t.z < 0 ? -v0.p : 0.0, b1 = t.w < 0 ? v1.p : 0.0;
+      const double b0 = hu ? 0.0 : -v0.p, b1 = hv ? 0.0 : v1.p;
       double2* dst = reinterpret_cast<double2*>(b + r);  // r even
       double2 v = make_double2(b0, b1);
       if (ACC) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
       NXFX_ST2(dst, v);
     }
     if (lhs) {
+      // the factorisation is built from cell_rh: it follows the matrix (ADD_VALUES included)
+      if (ACC) c.cell_rh[slot] += m; else NXFX_ST1(c.cell_rh + slot, m);
       const double m3 = __dmul_rn(m, kThird), m6 = __dmul_rn(m, kSixth);
-      const bool hu = t.z >= 0, hv = t.w >= 0;
       const bool ufirst = !hv || (hu && t.z < t.w);
       const int nl = (int)hu + (int)hv;
       // row u: [m/3, m/6 | +1 | (lam_u: -1) (lam_v: 0)]; row v: [m/6, m/3 | -1 | (lam_u: 0) (lam_v: +1)]
       const double u0 = (hu && ufirst) ? -1.0 : 0.0, u1 = ufirst ? 0.0 : -1.0;
       const double w0 = (hu && ufirst) ? 0.0 : 1.0, w1 = ufirst ? 1.0 : 0.0;
-      if (tnnz <= kAsmCap) {
-        double* s0 = sm + (sbase & 1) + start;
-        double* s1 = s0 + 3 + nl;
-        s0[0] = m3; s0[1] = m6; s0[2] = 1.0;
-        s1[0] = m6; s1[1] = m3; s1[2] = -1.0;
-        if (nl > 0) { s0[3] = u0; s1[3] = w0; }
-        if (nl > 1) { s0[4] = u1; s1[4] = w1; }
-      }  // tnnz <= 512 rows * 5 entries == kAsmCap always holds for N == 1
+      double* s0 = sm + (sbase & 1) + 6 * (int)threadIdx.x + 2 * pre;
+      double* s1 = s0 + 3 + nl;
+      s0[0] = m3; s0[1] = m6; s0[2] = 1.0;
+      s1[0] = m6; s1[1] = m3; s1[2] = -1.0;
+      if (nl > 0) { s0[3] = u0; s1[3] = w0; }
+      if (nl > 1) { s0[4] = u1; s1[4] = w1; }
     }
   }
-  if (lhs && tnnz <= kAsmCap) {
+  if (lhs) {  // tnnz <= 256 slots * 10 entries == kAsmCap always holds for N == 1
     __syncthreads();
     flush_tile<ACC>(sm, vals, sbase, tnnz);
   }
@@ -452,11 +476,11 @@ __device__ __forceinline__ void flux_tile_gen(const Net& g, const Coef& c, const
   const int lane = threadIdx.x & 31;
   const int rr = active ? r : g.ndofs;  // inactive lanes still take part in the shuffles
   if (d.tnnz > kAsmCap) {
-    if (lhs) assemble_row<ACC, false>(g, c, d, rr, d.sbase + d.start, lane, b, rhs, GlobalSink<ACC>{vals});
-    else assemble_row<ACC, false>(g, c, d, rr, 0, lane, b, rhs, [](bool, int, double) {});
+    if (lhs) assemble_row<ACC, false>(g, c, d, rr, d.sbase + d.start, lane, b, lhs, rhs, GlobalSink<ACC>{vals});
+    else assemble_row<ACC, false>(g, c, d, rr, 0, lane, b, lhs, rhs, [](bool, int, double) {});
     return;
   }
-  assemble_row<ACC, false>(g, c, d, rr, (d.sbase & 1) + d.start, lane, b, rhs, SmemSink{sm});
+  assemble_row<ACC, false>(g, c, d, rr, (d.sbase & 1) + d.start, lane, b, lhs, rhs, SmemSink{sm});
   if (lhs) {
     __syncthreads();
     flush_tile<ACC>(sm, vals, d.sbase, d.tnnz);

@@ -43,13 +43,24 @@ struct TreeSchedule {
   DevBuf<int32_t> bif_of_t, chunk_desc, t_inc_ptr;
   DevBuf<int2> t_inc;
   DevBuf<double> lam_nat;
-  DevBuf<int32_t> t_of_bif, t_parent, t_pedge, t_cptr, t_cidx, chunk_lptr, lvl_ptr, chord_edge;
+  DevBuf<int32_t> t_of_bif, t_parent, t_pedge, t_pslot, t_cptr, t_cidx, chunk_lptr, lvl_ptr, chord_edge;
   // numeric
   DevBuf<double> diag0, tg, d, gd, r, lam;  // schedule order
   bool fast_ok = false;                       // every chunk fits the shared-memory sweep kernel
   bool coop_ok = false;                       // all bottom chunks can be co-resident (single-launch solve)
   bool coop_fs_ok = false;                    // ... also with the larger buffers of the fused factor + solve
   unsigned int epoch = 0;
+};
+
+// One system matrix on the ctx's pattern: its own value array and the per-cell R*h that the network
+// Schur factorisation is built from.  The reference hands out independent PETSc Mats
+// (assembly.py:354, solver.py:43); every Mat of the Python layer owns one of these.
+struct MatState {
+  int64_t id = 0;
+  DevBuf<double> vals;     // [nnz + 8]
+  DevBuf<double> cell_rh;  // [nc] sum over the accumulated assemblies of R*h (N == 1: in flux-slot order)
+  bool assembled = false;
+  int acc_count = 0;  // number of lhs assemblies accumulated since the last zero (ADD_VALUES)
 };
 
 }  // namespace nxfx
@@ -63,7 +74,7 @@ struct nxfx_ctx {
   int sm_count = 148;
 
   // network
-  bool has_network = false, has_pattern = false, has_pbc = false, assembled = false, pc_ready = false;
+  bool has_network = false, has_pattern = false, has_pbc = false, pc_ready = false;
   bool bottom_factored = false;  // multi-GPU: nxfx_pc_setup_begin done (bottom chunks factorised)
   int32_t n_nodes = 0, E = 0, gdim = 0, N = 0, n_bif = 0, n_inc = 0;
   int64_t nv = 0, nc = 0, nq = 0, poff = 0, loff = 0, ndofs = 0, nnz = 0;
@@ -78,12 +89,17 @@ struct nxfx_ctx {
   bool generic = false;
   nxfx::DevBuf<int32_t> gen_src_id, gen_bptr, gen_bid;
   nxfx::DevBuf<double> gen_src_coef, gen_bcoef, gen_cell_h;
-  nxfx::DevBuf<double> vals;
-  nxfx::DevBuf<double> cell_rh;  // [nc] R*h per cell, written by the assembly kernel
+  std::vector<nxfx::MatState*> mats;  // every matrix created on the current pattern ([0] = default)
+  nxfx::MatState* cur = nullptr;      // the bound matrix: target of assemble, operator of spmv / solve
+  int64_t next_mat_id = 1;
+  bool pc_unscaled = false;           // inside the rescaled application for a k-fold accumulated matrix
+  int64_t pc_mat = -1;                // matrix the tree factors were computed from (valid iff pc_ready)
+  std::vector<int32_t> edge_slot_h;   // host copy (slot of the parent link edges of the schedule)
   // solver workspace
   nxfx::TreeSchedule tree;
   nxfx::DevBuf<double> edge_g, edge_c, edge_fn;  // [E] conductance, condensed rhs, F_N
   nxfx::DevBuf<double> work;                     // krylov vectors
+  nxfx::DevBuf<double> work2;                    // 2 vectors: solves with a k-fold accumulated matrix
   nxfx::DevBuf<double> scal;                     // device scalars / partials
   nxfx::DevBuf<unsigned int> ticket;  // [0] reductions, [1] tree sweeps, [2] tree epoch flag
   double* scal_h = nullptr;  // pinned mirror (mapped: kernels may store results into it)

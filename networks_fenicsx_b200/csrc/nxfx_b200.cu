@@ -52,6 +52,7 @@ TreeDev make_tree(nxfx_ctx* c) {
   t.cap = s.cap;
   t.t_parent = s.t_parent.p;
   t.t_pedge = s.t_pedge.p;
+  t.t_pslot = s.t_pslot.p;
   t.t_cptr = s.t_cptr.p;
   t.t_cidx = s.t_cidx.p;
   t.chunk_lptr = s.chunk_lptr.p;
@@ -89,6 +90,57 @@ int ensure_scal(nxfx_ctx* ctx) {
 
 double* slot(nxfx_ctx* ctx, int i) { return ctx->scal.p + kScalPartials + i; }
 
+bool is_assembled(const nxfx_ctx* ctx) { return ctx->cur && ctx->cur->assembled; }
+
+void release_matrices(nxfx_ctx* ctx) {
+  for (MatState* m : ctx->mats) delete m;
+  ctx->mats.clear();
+  ctx->cur = nullptr;
+  ctx->pc_ready = false;
+  ctx->pc_mat = -1;
+}
+
+// a zeroed matrix on the current pattern
+int new_matrix(nxfx_ctx* ctx, int64_t id, MatState** out) {
+  auto* m = new MatState();
+  m->id = id;
+  ctx->mats.push_back(m);
+  NXFX_CUDA(ctx, m->vals.alloc((size_t)ctx->nnz + 8));
+  NXFX_CUDA(ctx, cudaMemsetAsync(m->vals.p, 0, ((size_t)ctx->nnz + 8) * sizeof(double), ctx->stream));
+  NXFX_CUDA(ctx, m->cell_rh.alloc((size_t)ctx->nc));
+  NXFX_CUDA(ctx, cudaMemsetAsync(m->cell_rh.p, 0, (size_t)ctx->nc * sizeof(double), ctx->stream));
+  if (out) *out = m;
+  return NXFX_OK;
+}
+
+// k-fold accumulation (ADD_VALUES without zeroEntries): the solver needs the count, see do_pc_apply
+void note_lhs_assembled(nxfx_ctx* ctx, int accumulate) {
+  MatState* m = ctx->cur;
+  m->acc_count = (accumulate && m->assembled) ? m->acc_count + 1 : 1;
+  m->assembled = true;
+  ctx->pc_ready = false;
+  ctx->bottom_factored = false;
+}
+
+void bind_matrix(nxfx_ctx* ctx, MatState* m) {
+  if (ctx->cur != m) ctx->bottom_factored = false;
+  ctx->cur = m;
+  // the tree factors belong to ONE matrix: binding another one invalidates them
+  if (ctx->pc_ready && ctx->pc_mat != m->id) ctx->pc_ready = false;
+}
+
+// callers that never create a matrix (plain C users of the ABI) work on matrix 0
+int ensure_matrix(nxfx_ctx* ctx) {
+  if (ctx->cur) return NXFX_OK;
+  for (MatState* m : ctx->mats)
+    if (m->id == 0) { bind_matrix(ctx, m); return NXFX_OK; }
+  MatState* m = nullptr;
+  int rc = new_matrix(ctx, 0, &m);
+  if (rc) return rc;
+  bind_matrix(ctx, m);
+  return NXFX_OK;
+}
+
 int build_vertices(nxfx_ctx* ctx) {
   const int n3 = ctx->n_nodes * 3;
   NXFX_LAUNCH(ctx, pad_nodes_kernel, (int)cdiv(n3, kThreads), kThreads, 0, ctx->n_nodes, ctx->gdim,
@@ -113,12 +165,12 @@ int do_spmv(nxfx_ctx* ctx, const double* x, double* y) {
   if (ctx->pipe_ok) {
     const int grid = std::min(ntiles, ctx->sm_count * kPipeBlocksPerSM);
     NXFX_LAUNCH(ctx, spmv_pipe_kernel<0>, grid, kTileRows, kPipeSmem, (int)ctx->ndofs, ntiles,
-                ctx->rowptr.p, ctx->colidx.p, ctx->vals.p, ctx->tile_base.p, x, y, nullptr, nullptr,
+                ctx->rowptr.p, ctx->colidx.p, ctx->cur->vals.p, ctx->tile_base.p, x, y, nullptr, nullptr,
                 nullptr, nullptr);
     return NXFX_OK;
   }
   NXFX_LAUNCH(ctx, spmv_kernel<0>, ntiles, kTileRows, 0, (int)ctx->ndofs, ntiles, ctx->rowptr.p,
-              ctx->colidx.p, ctx->vals.p, x, y, nullptr, nullptr, nullptr, nullptr);
+              ctx->colidx.p, ctx->cur->vals.p, x, y, nullptr, nullptr, nullptr, nullptr);
   return NXFX_OK;
 }
 
@@ -129,7 +181,7 @@ int do_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, doub
   if (ctx->pipe_ok && !pdl) {
     const int grid = std::min(ntiles, ctx->sm_count * kPipeBlocksPerSM);
     NXFX_LAUNCH(ctx, spmv_pipe_kernel<1>, grid, kTileRows, kPipeSmem, (int)ctx->ndofs, ntiles,
-                ctx->rowptr.p, ctx->colidx.p, ctx->vals.p, ctx->tile_base.p, x, r, b, ctx->scal.p,
+                ctx->rowptr.p, ctx->colidx.p, ctx->cur->vals.p, ctx->tile_base.p, x, r, b, ctx->scal.p,
                 ctx->ticket.p, norm2_d);
     return NXFX_OK;
   }
@@ -148,7 +200,7 @@ int do_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, doub
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     NXFX_CUDA(ctx, cudaLaunchKernelEx(&cfg, spmv_pipe_kernel<1>, (int)ctx->ndofs, ntiles, (const int32_t*)ctx->rowptr.p,
-                                      (const int32_t*)ctx->colidx.p, (const double*)ctx->vals.p,
+                                      (const int32_t*)ctx->colidx.p, (const double*)ctx->cur->vals.p,
                                       (const int32_t*)ctx->tile_base.p, x, r, b, ctx->scal.p, ctx->ticket.p, norm2_d, 0,
                                       (const double*)nullptr, (const double*)nullptr));
     ctx->launches++;
@@ -156,7 +208,7 @@ int do_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, doub
   }
   const int grid = std::min(ntiles, kMaxPartials);
   NXFX_LAUNCH(ctx, spmv_kernel<1>, grid, kTileRows, 0, (int)ctx->ndofs, ntiles, ctx->rowptr.p,
-              ctx->colidx.p, ctx->vals.p, x, r, b, ctx->scal.p, ctx->ticket.p, norm2_d);
+              ctx->colidx.p, ctx->cur->vals.p, x, r, b, ctx->scal.p, ctx->ticket.p, norm2_d);
   return NXFX_OK;
 }
 
@@ -232,10 +284,10 @@ int tree_pass(nxfx_ctx* ctx, bool factor, const double* fuse_r = nullptr, bool f
     FusedN1 fin{make_net(ctx), nullptr, nullptr};
     if (did_fuse) *did_fuse = false;
     if (factor) {
-      if (fuse) { fin.cell_rh = ctx->cell_rh.p; if (did_fuse) *did_fuse = true; }
+      if (fuse) { fin.cell_rh = ctx->cur->cell_rh.p; if (did_fuse) *did_fuse = true; }
       NXFX_LAUNCH(ctx, tree_factor_kernel, grid, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, tk, 1, fin);
     } else if (s.coop_ok && nb > 0) {
-      if (fuse) { fin.r = fuse_r; fin.cell_rh = ctx->cell_rh.p; if (did_fuse) *did_fuse = true; }
+      if (fuse) { fin.r = fuse_r; fin.cell_rh = ctx->cur->cell_rh.p; if (did_fuse) *did_fuse = true; }
       unsigned int* fl = ctx->ticket.p + 2;
       unsigned int ep = ++s.epoch;
       int nbv = nb;
@@ -261,12 +313,12 @@ int tree_pass(nxfx_ctx* ctx, bool factor, const double* fuse_r = nullptr, bool f
 }
 
 int do_pc_setup(nxfx_ctx* ctx) {
-  NXFX_REQUIRE(ctx, ctx->assembled, "assemble the matrix before pc_setup");
+  NXFX_REQUIRE(ctx, is_assembled(ctx), "assemble the matrix before pc_setup");
   NXFX_REQUIRE(ctx, ctx->tree.set, "nxfx_set_tree_schedule has not been called");
   const bool n1 = ctx->N == 1 && ctx->tree.fast_ok;  // (the global-memory fallback sweeps read edge_g)
   if (!n1)
     NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N,
-                ctx->cell_rh.p, ctx->edge_g.p);
+                ctx->cur->cell_rh.p, ctx->edge_g.p);
   if (ctx->n_bif > 0) {
     if (!n1) {
       NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx),
@@ -276,23 +328,24 @@ int do_pc_setup(nxfx_ctx* ctx) {
     if (rc) return rc;
   }
   ctx->pc_ready = true;
+  ctx->pc_mat = ctx->cur->id;
   return NXFX_OK;
 }
 
 // factorisation and first application z = P^{-1} r in one cooperative launch (N == 1, single GPU)
 bool can_fuse_setup(const nxfx_ctx* ctx) {
   return ctx->N == 1 && ctx->tree.set && ctx->tree.fast_ok && ctx->tree.coop_fs_ok && ctx->n_bif > 0 &&
-         ctx->tree.n_chunks > 1 && !ctx->lam_weight.p;
+         ctx->tree.n_chunks > 1 && !ctx->lam_weight.p && ctx->cur->acc_count == 1;
 }
 
 int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z) {
-  NXFX_REQUIRE(ctx, ctx->assembled, "assemble the matrix before pc_setup");
+  NXFX_REQUIRE(ctx, is_assembled(ctx), "assemble the matrix before pc_setup");
   NXFX_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(r) & 15) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0,
                "vectors must be 16-byte aligned");
   auto& s = ctx->tree;
   Net g = make_net(ctx);
   TreeDev t = make_tree(ctx);
-  FusedN1 fin{g, r, ctx->cell_rh.p};
+  FusedN1 fin{g, r, ctx->cur->cell_rh.p};
   unsigned int* tk = ctx->ticket.p + 1;
   unsigned int* fl = ctx->ticket.p + 2;
   unsigned int ep = ++s.epoch;
@@ -322,19 +375,42 @@ int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z) {
   NXFX_CUDA(ctx, le);
   ctx->launches++;
   ctx->pc_ready = true;
+  ctx->pc_mat = ctx->cur->id;
   cudaLaunchConfig_t bc = {};
   bc.gridDim = dim3((unsigned)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads));
   bc.blockDim = dim3(kThreads);
   bc.stream = ctx->stream;
   bc.attrs = attr + 1;
   bc.numAttrs = 1;
-  NXFX_CUDA(ctx, cudaLaunchKernelEx(&bc, edge_backsub_n1_kernel<false>, g, t, (const double*)ctx->cell_rh.p, r, z));
+  NXFX_CUDA(ctx, cudaLaunchKernelEx(&bc, edge_backsub_n1_kernel<false>, g, t, (const double*)ctx->cur->cell_rh.p, r, z));
   ctx->launches++;
   return NXFX_OK;
 }
 
 int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add = false) {
   const int n = (int)ctx->ndofs;
+  if (pc_type == NXFX_PC_NETWORK_SCHUR && ctx->cur->acc_count > 1 && !ctx->pc_unscaled) {
+    // The matrix holds k accumulated assemblies: A_k = [M_sum, -k B^T, k T^T; k B, 0, 0; k T, 0, 0] with
+    // M_sum built from the accumulated cell_rh.  With p' = k p, lam' = k lam this is the standard
+    // operator on M_sum with the constraint right-hand sides divided by k:
+    //   z' = P(M_sum)^{-1} (r_q, r_p / k, r_lam / k),   z = (z'_q, z'_p / k, z'_lam / k).
+    const size_t ld = vec_stride(ctx);
+    if (ctx->work2.n < 2 * ld) {
+      NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      NXFX_CUDA(ctx, ctx->work2.alloc(2 * ld));
+    }
+    const double inv_k = 1.0 / (double)ctx->cur->acc_count;
+    double* rs = ctx->work2.p;
+    double* zs = ctx->work2.p + ld;
+    NXFX_LAUNCH(ctx, scale_tail_kernel<false>, vec_grid(ctx, n), kThreads, 0, n, (int)ctx->poff, inv_k, r, rs);
+    ctx->pc_unscaled = true;
+    const int rc = do_pc_apply(ctx, pc_type, rs, zs, false);
+    ctx->pc_unscaled = false;
+    if (rc) return rc;
+    if (add) NXFX_LAUNCH(ctx, scale_tail_kernel<true>, vec_grid(ctx, n), kThreads, 0, n, (int)ctx->poff, inv_k, zs, z);
+    else NXFX_LAUNCH(ctx, scale_tail_kernel<false>, vec_grid(ctx, n), kThreads, 0, n, (int)ctx->poff, inv_k, zs, z);
+    return NXFX_OK;
+  }
   if (add && pc_type != NXFX_PC_NETWORK_SCHUR) {  // generic: z_tmp = P^{-1} r, z += z_tmp
     int rc = ensure_work(ctx, 3);
     if (rc) return rc;
@@ -349,7 +425,7 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
   }
   if (pc_type == NXFX_PC_JACOBI_FLUX) {
     NXFX_LAUNCH(ctx, jacobi_flux_kernel, (int)cdiv(n, kThreads), kThreads, 0, n, (int)ctx->nq,
-                ctx->rowptr.p, ctx->colidx.p, ctx->vals.p, r, z);
+                ctx->rowptr.p, ctx->colidx.p, ctx->cur->vals.p, r, z);
     return NXFX_OK;
   }
   NXFX_REQUIRE(ctx, ctx->pc_ready, "pc_setup has not been run");
@@ -364,16 +440,16 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
       // single-launch solve: the tree kernel evaluates the bifurcation right-hand sides itself
       const bool fuse = ctx->tree.coop_ok && ctx->tree.n_chunks > 1 && !ctx->lam_weight.p;
       if (!fuse)
-        NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cell_rh.p,
+        NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cur->cell_rh.p,
                     ctx->lam_weight.p);
       int rc = tree_pass(ctx, false, r, fuse);
       if (rc) return rc;
     }
-    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
-    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, z);
+    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, z);
     return NXFX_OK;
   }
-  NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p,
+  NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cur->cell_rh.p,
               r, ctx->edge_c.p, ctx->edge_fn.p);
   if (ctx->n_bif > 0) {
     NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r,
@@ -382,9 +458,9 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
     if (rc) return rc;
   }
   if (add)
-    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
   else
-    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
   return NXFX_OK;
 }
 
@@ -585,6 +661,7 @@ int nxfx_destroy(nxfx_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->scal_h) cudaFreeHost(ctx->scal_h);
+  release_matrices(ctx);
   delete ctx;
   return NXFX_OK;
 }
@@ -692,7 +769,9 @@ int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gd
   for (int32_t k = 0; k < n_inc; ++k)
     if ((bif_inc[k] >> 1) < 0 || (bif_inc[k] >> 1) >= E)
       return fail(ctx, NXFX_ERR_INVALID, "bif_inc[%d] out of range", k);
-  ctx->has_network = ctx->has_pattern = ctx->has_pbc = ctx->assembled = ctx->pc_ready = false;
+  ctx->has_network = ctx->has_pattern = ctx->has_pbc = ctx->pc_ready = false;
+  release_matrices(ctx);
+  ctx->edge_slot_h.assign(edge_slot, edge_slot + E);
   ctx->n_shared = 0;
   ctx->shared_lm.release();
   ctx->lam_weight.release();
@@ -712,7 +791,6 @@ int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gd
   if ((rc = upload(ctx, ctx->bif_inc, bif_inc, (size_t)n_inc))) return rc;
   NXFX_CUDA(ctx, ctx->x.alloc((size_t)nv * 4));
   NXFX_CUDA(ctx, cudaMemsetAsync(ctx->x.p, 0, (size_t)nv * 4 * sizeof(double), ctx->stream));
-  NXFX_CUDA(ctx, ctx->cell_rh.alloc((size_t)nc));
   NXFX_CUDA(ctx, ctx->edge_g.alloc((size_t)E));
   NXFX_CUDA(ctx, ctx->edge_c.alloc((size_t)E));
   NXFX_CUDA(ctx, ctx->edge_fn.alloc((size_t)E));
@@ -772,22 +850,82 @@ int nxfx_symbolic(nxfx_ctx* ctx) {
   NXFX_REQUIRE(ctx, nnz > 0, "pattern overflow (nnz does not fit int32)");
   ctx->nnz = nnz;
   NXFX_CUDA(ctx, ctx->colidx.alloc((size_t)nnz + 8));
-  NXFX_CUDA(ctx, ctx->vals.alloc((size_t)nnz + 8));
   NXFX_CUDA(ctx, cudaMemsetAsync(ctx->colidx.p, 0, ((size_t)nnz + 8) * sizeof(int32_t), ctx->stream));
-  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->vals.p, 0, ((size_t)nnz + 8) * sizeof(double), ctx->stream));
   NXFX_LAUNCH(ctx, fill_cols_kernel, (int)cdiv(n, kThreads), kThreads, 0, g, ctx->rowptr.p, ctx->colidx.p);
   if ((rc = setup_spmv_tiles(ctx))) return rc;
+  release_matrices(ctx);  // a new pattern: matrices of the previous one are gone (matrix 0 is created on demand)
   ctx->has_pattern = true;
-  ctx->assembled = false;
+  return NXFX_OK;
+}
+
+int nxfx_matrix_create(nxfx_ctx* ctx, int64_t* mat_id) {
+  if (!ctx || !mat_id) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
+  MatState* m = nullptr;
+  int rc = new_matrix(ctx, ctx->next_mat_id++, &m);
+  if (rc) return rc;
+  *mat_id = m->id;
+  return NXFX_OK;
+}
+
+static MatState* find_matrix(nxfx_ctx* ctx, int64_t id) {
+  for (MatState* m : ctx->mats)
+    if (m->id == id) return m;
+  return nullptr;
+}
+
+int nxfx_matrix_destroy(nxfx_ctx* ctx, int64_t mat_id) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  for (size_t i = 0; i < ctx->mats.size(); ++i) {
+    if (ctx->mats[i]->id != mat_id) continue;
+    NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->cur == ctx->mats[i]) { ctx->cur = nullptr; ctx->bottom_factored = false; }
+    if (ctx->pc_mat == mat_id) { ctx->pc_ready = false; ctx->pc_mat = -1; }
+    delete ctx->mats[i];
+    ctx->mats.erase(ctx->mats.begin() + (long)i);
+    return NXFX_OK;
+  }
+  return NXFX_OK;  // already gone with its pattern
+}
+
+int nxfx_matrix_bind(nxfx_ctx* ctx, int64_t mat_id) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  MatState* m = find_matrix(ctx, mat_id);
+  if (!m) return fail(ctx, NXFX_ERR_INVALID, "nxfx_matrix_bind: matrix %lld does not exist on the current pattern", (long long)mat_id);
+  bind_matrix(ctx, m);
+  return NXFX_OK;
+}
+
+int nxfx_matrix_zero(nxfx_ctx* ctx) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
+  { int rc = ensure_matrix(ctx); if (rc) return rc; }
+  MatState* m = ctx->cur;
+  NXFX_CUDA(ctx, cudaMemsetAsync(m->vals.p, 0, m->vals.n * sizeof(double), ctx->stream));
+  NXFX_CUDA(ctx, cudaMemsetAsync(m->cell_rh.p, 0, m->cell_rh.n * sizeof(double), ctx->stream));
+  m->assembled = false;
+  m->acc_count = 0;
+  if (ctx->pc_mat == m->id) ctx->pc_ready = false;
+  return NXFX_OK;
+}
+
+int nxfx_matrix_info(nxfx_ctx* ctx, int64_t* mat_id, int32_t* assembled, int32_t* acc_count) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
+  { int rc = ensure_matrix(ctx); if (rc) return rc; }
+  if (mat_id) *mat_id = ctx->cur->id;
+  if (assembled) *assembled = ctx->cur->assembled;
+  if (acc_count) *acc_count = ctx->cur->acc_count;
   return NXFX_OK;
 }
 
 int nxfx_csr_device(nxfx_ctx* ctx, const int32_t** rowptr, const int32_t** colidx, double** vals) {
   if (!ctx) return NXFX_ERR_INVALID;
   NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
+  { int rc = ensure_matrix(ctx); if (rc) return rc; }
   if (rowptr) *rowptr = ctx->rowptr.p;
   if (colidx) *colidx = ctx->colidx.p;
-  if (vals) *vals = ctx->vals.p;
+  if (vals) *vals = ctx->cur->vals.p;
   return NXFX_OK;
 }
 
@@ -808,23 +946,24 @@ int nxfx_assemble(nxfx_ctx* ctx, const double* R_cell, double R_const, const dou
   NXFX_REQUIRE(ctx, !rhs || (b && ctx->has_pbc), "rhs requested without b / boundary pressure");
   NXFX_REQUIRE(ctx, !rhs || (reinterpret_cast<uintptr_t>(b) & 15) == 0, "b must be 16-byte aligned");
   if (!lhs && !rhs) return NXFX_OK;
+  { int rc = ensure_matrix(ctx); if (rc) return rc; }
   Net g = make_net(ctx);
   Coef c;
   c.R_cell = R_cell; c.f_cell = f_cell; c.R_const = R_const; c.f_const = f_const;
-  c.cell_rh = ctx->cell_rh.p;
+  c.cell_rh = ctx->cur->cell_rh.p;
   const bool n1 = ctx->N == 1;
   const int nft = (int)cdiv(ctx->nq, n1 ? kFluxRowsN1 : kTileRows);
   const int npt = (int)cdiv(ctx->nc, kPresRows);
   const int nlt = (int)cdiv(ctx->n_bif, kLamRows);
   const int grid = nft + npt + nlt;
   if (accumulate) {
-    if (n1) NXFX_LAUNCH(ctx, (assemble_tiles_kernel<true, true>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs, nft, npt);
-    else NXFX_LAUNCH(ctx, (assemble_tiles_kernel<true, false>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs, nft, npt);
+    if (n1) NXFX_LAUNCH(ctx, (assemble_tiles_kernel<true, true>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->cur->vals.p, b, lhs, rhs, nft, npt);
+    else NXFX_LAUNCH(ctx, (assemble_tiles_kernel<true, false>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->cur->vals.p, b, lhs, rhs, nft, npt);
   } else {
-    if (n1) NXFX_LAUNCH(ctx, (assemble_tiles_kernel<false, true>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs, nft, npt);
-    else NXFX_LAUNCH(ctx, (assemble_tiles_kernel<false, false>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->vals.p, b, lhs, rhs, nft, npt);
+    if (n1) NXFX_LAUNCH(ctx, (assemble_tiles_kernel<false, true>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->cur->vals.p, b, lhs, rhs, nft, npt);
+    else NXFX_LAUNCH(ctx, (assemble_tiles_kernel<false, false>), grid, kTileRows, 0, g, c, ctx->rowptr.p, ctx->cur->vals.p, b, lhs, rhs, nft, npt);
   }
-  if (lhs) { ctx->assembled = true; ctx->pc_ready = false; ctx->bottom_factored = false; }
+  if (lhs) note_lhs_assembled(ctx, accumulate);
   return NXFX_OK;
 }
 
@@ -873,6 +1012,12 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
   }
   if ((rc = upload(ctx, s.t_parent, t_parent, nb))) return rc;
   if ((rc = upload(ctx, s.t_pedge, t_pedge, nb))) return rc;
+  {
+    std::vector<int32_t> pslot(nb);
+    for (size_t t = 0; t < nb; ++t) pslot[t] = t_pedge[t] >= 0 ? ctx->edge_slot_h[t_pedge[t]] : -1;
+    if ((rc = upload(ctx, s.t_pslot, pslot.data(), nb))) return rc;
+    NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pslot goes out of scope
+  }
   if ((rc = upload(ctx, s.t_cptr, t_cptr, nb + 1))) return rc;
   if ((rc = upload(ctx, s.t_cidx, t_cidx, (size_t)t_cptr[nb]))) return rc;
   if ((rc = upload(ctx, s.chunk_lptr, chunk_lptr, (size_t)n_chunks + 1))) return rc;
@@ -957,13 +1102,16 @@ int nxfx_pc_apply(nxfx_ctx* ctx, const double* r, double* z) {
 int nxfx_spmv(nxfx_ctx* ctx, const double* x, double* y) {
   if (!ctx || !x || !y) return NXFX_ERR_INVALID;
   NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
+  { int rc = ensure_matrix(ctx); if (rc) return rc; }
   return do_spmv(ctx, x, y);
 }
 
 int nxfx_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, double* norm2) {
   if (!ctx || !b || !x || !r) return NXFX_ERR_INVALID;
   NXFX_REQUIRE(ctx, ctx->has_pattern, "symbolic phase has not been run");
-  int rc = do_residual(ctx, b, x, r, slot(ctx, 0));
+  int rc = ensure_matrix(ctx);
+  if (rc) return rc;
+  rc = do_residual(ctx, b, x, r, slot(ctx, 0));
   if (rc) return rc;
   if (norm2) {
     NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->scal_h, slot(ctx, 0), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -975,7 +1123,7 @@ int nxfx_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, do
 
 int nxfx_solve(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts* opts, nxfx_solve_info* info) {
   if (!ctx || !b || !x || !opts || !info) return NXFX_ERR_INVALID;
-  NXFX_REQUIRE(ctx, ctx->assembled, "matrix has not been assembled");
+  NXFX_REQUIRE(ctx, is_assembled(ctx), "matrix has not been assembled");
   std::memset(info, 0, sizeof *info);
   int rc;
   if (opts->pc_type == NXFX_PC_NETWORK_SCHUR && ctx->generic)
@@ -1043,7 +1191,8 @@ int nxfx_set_generic_system(nxfx_ctx* ctx, int32_t n_dofs, int32_t n_flux_rows, 
     if (i < 0 || (i & (kVertexFlag - 1)) >= lim) return fail(ctx, NXFX_ERR_INVALID, "bsrc_id[%d] out of range", k);
   }
   int rc;
-  ctx->has_pattern = ctx->assembled = ctx->pc_ready = false;
+  ctx->has_pattern = ctx->pc_ready = false;
+  release_matrices(ctx);
   ctx->ndofs = n_dofs; ctx->nq = n_flux_rows; ctx->nnz = nnz;
   ctx->poff = n_flux_rows; ctx->loff = n_dofs - ctx->n_bif;
   NXFX_CUDA(ctx, ctx->rowptr.alloc((size_t)n_dofs + 9));
@@ -1052,8 +1201,6 @@ int nxfx_set_generic_system(nxfx_ctx* ctx, int32_t n_dofs, int32_t n_flux_rows, 
   NXFX_CUDA(ctx, ctx->colidx.alloc((size_t)nnz + 8));
   NXFX_CUDA(ctx, cudaMemsetAsync(ctx->colidx.p, 0, ((size_t)nnz + 8) * sizeof(int32_t), ctx->stream));
   NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->colidx.p, colidx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-  NXFX_CUDA(ctx, ctx->vals.alloc((size_t)nnz + 8));
-  NXFX_CUDA(ctx, cudaMemsetAsync(ctx->vals.p, 0, ((size_t)nnz + 8) * sizeof(double), ctx->stream));
   if ((rc = upload(ctx, ctx->gen_src_id, src_id, (size_t)2 * nnz))) return rc;
   if ((rc = upload(ctx, ctx->gen_src_coef, src_coef, (size_t)2 * nnz))) return rc;
   if ((rc = upload(ctx, ctx->gen_bptr, bsrc_ptr, (size_t)n_dofs + 1))) return rc;
@@ -1072,6 +1219,7 @@ int nxfx_assemble_generic(nxfx_ctx* ctx, const double* R_cell, double R_const, c
   NXFX_REQUIRE(ctx, ctx->has_pattern && ctx->generic, "nxfx_set_generic_system has not been called");
   NXFX_REQUIRE(ctx, !rhs || (b && ctx->has_pbc), "rhs requested without b / boundary pressure");
   if (!lhs && !rhs) return NXFX_OK;
+  { int rc = ensure_matrix(ctx); if (rc) return rc; }
   Net g = make_net(ctx);
   NXFX_LAUNCH(ctx, cell_length_kernel, vec_grid(ctx, ctx->nc), kThreads, 0, g, ctx->gen_cell_h.p);
   if (lhs) {
@@ -1079,12 +1227,11 @@ int nxfx_assemble_generic(nxfx_ctx* ctx, const double* R_cell, double R_const, c
     const double2* sco = reinterpret_cast<const double2*>(ctx->gen_src_coef.p);
     if (accumulate)
       NXFX_LAUNCH(ctx, assemble_generic_kernel<true>, vec_grid(ctx, ctx->nnz), kThreads, 0, ctx->nnz, sid, sco,
-                  ctx->gen_cell_h.p, R_cell, R_const, ctx->vals.p);
+                  ctx->gen_cell_h.p, R_cell, R_const, ctx->cur->vals.p);
     else
       NXFX_LAUNCH(ctx, assemble_generic_kernel<false>, vec_grid(ctx, ctx->nnz), kThreads, 0, ctx->nnz, sid, sco,
-                  ctx->gen_cell_h.p, R_cell, R_const, ctx->vals.p);
-    ctx->assembled = true;
-    ctx->pc_ready = false;
+                  ctx->gen_cell_h.p, R_cell, R_const, ctx->cur->vals.p);
+    note_lhs_assembled(ctx, accumulate);
   }
   if (rhs) {
     const int n = (int)ctx->ndofs;
@@ -1120,6 +1267,8 @@ int nxfx_set_shared(nxfx_ctx* ctx, int32_t n_shared, const int32_t* shared_lm, c
 static int dist_ready(nxfx_ctx* ctx, const double* buf) {
   NXFX_REQUIRE(ctx, ctx->tree.set && ctx->tree.fast_ok && ctx->tree.n_chunks >= 1 && buf,
                "needs a tree schedule that fits the shared-memory sweeps and a buffer");
+  NXFX_REQUIRE(ctx, ctx->cur && ctx->cur->acc_count <= 1,
+               "the partitioned solve does not take a matrix accumulated over several assemblies");
   return NXFX_OK;
 }
 
@@ -1134,14 +1283,14 @@ int nxfx_pc_setup_begin(nxfx_ctx* ctx, double* buf) {
   if (!ctx) return NXFX_ERR_INVALID;
   int rc = dist_ready(ctx, buf);
   if (rc) return rc;
-  NXFX_REQUIRE(ctx, ctx->assembled, "assemble the matrix before pc_setup");
+  NXFX_REQUIRE(ctx, is_assembled(ctx), "assemble the matrix before pc_setup");
   auto& s = ctx->tree;
   TreeDev t = make_tree(ctx);
   const int nb = s.n_chunks - 1;
   if (ctx->N == 1) {
-    NXFX_LAUNCH(ctx, bif_diag_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx), t, ctx->cell_rh.p);
+    NXFX_LAUNCH(ctx, bif_diag_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx), t, ctx->cur->cell_rh.p);
   } else {
-    NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N, ctx->cell_rh.p, ctx->edge_g.p);
+    NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N, ctx->cur->cell_rh.p, ctx->edge_g.p);
     NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, make_net(ctx), t, ctx->edge_g.p);
   }
   if (nb > 0) NXFX_LAUNCH(ctx, tree_factor_kernel, nb, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, ctx->ticket.p + 1, 0,
@@ -1157,6 +1306,7 @@ int nxfx_pc_setup_end(nxfx_ctx* ctx, double* buf) {
   if (rc) return rc;
   NXFX_LAUNCH(ctx, (tree_top_kernel<true, kFinish>), 1, kTreeThreads, tree_smem_bytes(ctx->tree.cap), make_tree(ctx), ctx->tree.n_chunks - 1, buf);
   ctx->pc_ready = true;
+  ctx->pc_mat = ctx->cur->id;
   return NXFX_OK;
 }
 
@@ -1172,9 +1322,9 @@ int nxfx_pc_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
   TreeDev t = make_tree(ctx);
   const int nb = ctx->tree.n_chunks - 1;
   if (ctx->N == 1) {
-    NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cell_rh.p, ctx->lam_weight.p);
+    NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cur->cell_rh.p, ctx->lam_weight.p);
   } else {
-    NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cell_rh.p, r, ctx->edge_c.p, ctx->edge_fn.p);
+    NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cur->cell_rh.p, r, ctx->edge_c.p, ctx->edge_fn.p);
     NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->edge_g.p, ctx->edge_c.p,
                 ctx->edge_fn.p, ctx->lam_weight.p);
   }
@@ -1194,14 +1344,14 @@ int nxfx_pc_apply_end(nxfx_ctx* ctx, const double* r, double* z, double* buf, in
   if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, ctx->ticket.p + 1, 0);
   const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
   if (ctx->N == 1) {
-    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
-    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+    if (add) NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, z);
+    else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, z);
     return NXFX_OK;
   }
   if (add)
-    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
   else
-    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+    NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
   return NXFX_OK;
 }
 
@@ -1212,7 +1362,7 @@ int nxfx_pc_setup_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
   if (!ctx || !r) return NXFX_ERR_INVALID;
   int rc = dist_ready(ctx, buf);
   if (rc) return rc;
-  NXFX_REQUIRE(ctx, ctx->assembled, "assemble the matrix before pc_setup");
+  NXFX_REQUIRE(ctx, is_assembled(ctx), "assemble the matrix before pc_setup");
   const int nt = std::max(ctx->tree.n_top, 1);
   if (ctx->N != 1) {
     if ((rc = nxfx_pc_setup_begin(ctx, buf))) return rc;
@@ -1222,7 +1372,7 @@ int nxfx_pc_setup_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
   auto& s = ctx->tree;
   TreeDev t = make_tree(ctx);
   const int nb = s.n_chunks - 1;
-  FusedN1 fin{make_net(ctx), r, ctx->cell_rh.p, ctx->lam_weight.p};
+  FusedN1 fin{make_net(ctx), r, ctx->cur->cell_rh.p, ctx->lam_weight.p};
   const size_t smem = tree_smem_bytes_fs(s.cap);
   if (nb > 0) NXFX_LAUNCH(ctx, tree_factor_solve_bottom_kernel, nb, kTreeThreads, smem, t, fin);
   NXFX_LAUNCH(ctx, tree_top_fs_kernel<kPartial>, 1, kTreeThreads, smem, t, nb, buf, fin);
@@ -1244,12 +1394,13 @@ int nxfx_pc_setup_apply_end(nxfx_ctx* ctx, const double* r, double* z, double* b
   Net g = make_net(ctx);
   TreeDev t = make_tree(ctx);
   const int nb = s.n_chunks - 1;
-  FusedN1 fin{g, r, ctx->cell_rh.p, ctx->lam_weight.p};
+  FusedN1 fin{g, r, ctx->cur->cell_rh.p, ctx->lam_weight.p};
   NXFX_LAUNCH(ctx, tree_top_fs_kernel<kFinish>, 1, kTreeThreads, tree_smem_bytes_fs(s.cap), t, nb, buf, fin);
   ctx->pc_ready = true;
+  ctx->pc_mat = ctx->cur->id;
   if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, tree_smem_bytes(s.cap), t, nb, ctx->ticket.p + 1, 0);
   const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
-  NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cell_rh.p, r, z);
+  NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, z);
   return NXFX_OK;
 }
 
@@ -1272,12 +1423,13 @@ int nxfx_unpack_shared(nxfx_ctx* ctx, const double* buf, double* v) {
 int nxfx_residual_partial(nxfx_ctx* ctx, const double* b, const double* x, double* r, double* buf) {
   if (!ctx || !b || !x || !r || !buf) return NXFX_ERR_INVALID;
   NXFX_REQUIRE(ctx, ctx->has_pattern && ctx->lam_nonshared.p, "nxfx_set_shared has not been called");
+  NXFX_REQUIRE(ctx, is_assembled(ctx), "matrix has not been assembled");
   int rc;
   if (ctx->pipe_ok) {  // the weighted partial norms come out of the residual kernel itself
     const int ntiles = (int)cdiv(ctx->ndofs, kTileRows);
     const int grid = std::min(ntiles, ctx->sm_count * kPipeBlocksPerSM);
     NXFX_LAUNCH(ctx, spmv_pipe_kernel<2>, grid, kTileRows, kPipeSmem, (int)ctx->ndofs, ntiles, ctx->rowptr.p,
-                ctx->colidx.p, ctx->vals.p, ctx->tile_base.p, x, r, b, ctx->scal.p, ctx->ticket.p,
+                ctx->colidx.p, ctx->cur->vals.p, ctx->tile_base.p, x, r, b, ctx->scal.p, ctx->ticket.p,
                 buf + ctx->n_shared, (int)ctx->loff, ctx->lam_nonshared.p, ctx->lam_weight.p);
     return nxfx_pack_shared(ctx, r, buf);
   }
@@ -1310,5 +1462,27 @@ int nxfx_global_flux(nxfx_ctx* ctx, const double* x, double* out) {
   NXFX_LAUNCH(ctx, global_flux_kernel, vec_grid(ctx, ctx->nc), kThreads, 0, make_net(ctx), x, out);
   return NXFX_OK;
 }
+
+#ifdef NXFX_TREE_STAMPS
+// development builds only (not part of include/nxfx_b200.h)
+int nxfx_debug_tree_stamps(nxfx_ctx* ctx, unsigned long long* out32) {
+  if (!ctx || !out32) return NXFX_ERR_INVALID;
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  NXFX_CUDA(ctx, cudaMemcpyFromSymbol(out32, g_tree_stamps, 32 * sizeof(unsigned long long)));
+  return NXFX_OK;
+}
+int nxfx_debug_device_attrs(nxfx_ctx* ctx, int* out8) {
+  if (!ctx || !out8) return NXFX_ERR_INVALID;
+  cudaDeviceGetAttribute(out8 + 0, cudaDevAttrL2CacheSize, ctx->device);
+  cudaDeviceGetAttribute(out8 + 1, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+  cudaDeviceGetAttribute(out8 + 2, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+  cudaDeviceGetAttribute(out8 + 3, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device);
+  cudaDeviceGetAttribute(out8 + 4, cudaDevAttrMultiProcessorCount, ctx->device);
+  cudaDeviceGetAttribute(out8 + 5, cudaDevAttrCanUseHostPointerForRegisteredMem, ctx->device);
+  cudaDeviceGetAttribute(out8 + 6, cudaDevAttrClusterLaunch, ctx->device);
+  cudaDeviceGetAttribute(out8 + 7, cudaDevAttrMemoryPoolsSupported, ctx->device);
+  return NXFX_OK;
+}
+#endif
 
 }  // extern "C"

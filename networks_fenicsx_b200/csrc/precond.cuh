@@ -26,6 +26,7 @@ struct TreeDev {
   const int32_t* __restrict__ bif_of_t;
   const int32_t* __restrict__ t_parent;
   const int32_t* __restrict__ t_pedge;
+  const int32_t* __restrict__ t_pslot;  // flux slot of t_pedge (N == 1: cell_rh is stored in slot order)
   const int32_t* __restrict__ t_cptr;
   const int32_t* __restrict__ t_cidx;
   const int32_t* __restrict__ chunk_lptr;
@@ -53,6 +54,22 @@ struct FusedN1 {
   const double* lam_weight = nullptr;  // multi-GPU: weight of this rank's copy of a multiplier row
 };
 
+// Development aid (-DNXFX_TREE_STAMPS): %globaltimer stamps of the phases of the fused tree kernel, taken by
+// thread 0 of block 0 (slots 0..15) and of the top-chunk block (slots 16..31).
+#ifdef NXFX_TREE_STAMPS
+__device__ unsigned long long g_tree_stamps[32];
+__device__ __forceinline__ void tree_stamp(bool top, int k) {
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || top)) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_tree_stamps[(top ? 16 : 0) + k] = t;
+  }
+}
+#define NXFX_STAMP(top, k) tree_stamp((top), (k))
+#else
+#define NXFX_STAMP(top, k) ((void)0)
+#endif
+
 // n = node in schedule order; its incidences come from the schedule-ordered table (two dependent
 // loads instead of the five of bif_of_t -> bif_ptr -> bif_inc -> edge_slot -> r)
 __device__ __forceinline__ double n1_node_rhs(const FusedN1& f, const TreeDev& t, int n) {
@@ -61,7 +78,7 @@ __device__ __forceinline__ double n1_node_rhs(const FusedN1& f, const TreeDev& t
   for (int k = t.t_inc_ptr[n]; k < t.t_inc_ptr[n + 1]; ++k) {
     const int2 inc = t.t_inc[k];
     const double2 rq = *reinterpret_cast<const double2*>(f.r + (inc.x & ~1));
-    const double rp = f.r[f.g.poff + inc.y], rh = f.cell_rh[inc.y];
+    const double rp = f.r[f.g.poff + inc.y], rh = f.cell_rh[inc.x >> 1];
     const double gc = ((rq.x + rq.y) - 0.5 * rh * rp) / rh;
     s += (inc.x & 1) ? (rp + gc) : -gc;
   }
@@ -76,7 +93,7 @@ __device__ __forceinline__ double n1_node_rhs_diag(const FusedN1& f, const TreeD
   for (int k = t.t_inc_ptr[n]; k < t.t_inc_ptr[n + 1]; ++k) {
     const int2 inc = t.t_inc[k];
     const double2 rq = *reinterpret_cast<const double2*>(f.r + (inc.x & ~1));
-    const double rp = f.r[f.g.poff + inc.y], rh = f.cell_rh[inc.y];
+    const double rp = f.r[f.g.poff + inc.y], rh = f.cell_rh[inc.x >> 1];
     const double gc = ((rq.x + rq.y) - 0.5 * rh * rp) / rh;
     s += (inc.x & 1) ? (rp + gc) : -gc;
     d += 1.0 / rh;
@@ -87,7 +104,7 @@ __device__ __forceinline__ double n1_node_rhs_diag(const FusedN1& f, const TreeD
 
 __device__ __forceinline__ double n1_node_diag(const FusedN1& f, const TreeDev& t, int n) {
   double s = 0.0;
-  for (int k = t.t_inc_ptr[n]; k < t.t_inc_ptr[n + 1]; ++k) s += 1.0 / f.cell_rh[t.t_inc[k].y];
+  for (int k = t.t_inc_ptr[n]; k < t.t_inc_ptr[n + 1]; ++k) s += 1.0 / f.cell_rh[t.t_inc[k].x >> 1];
   return s;
 }
 
@@ -309,7 +326,7 @@ __device__ __forceinline__ void factor_chunk(const TreeDev& t, const TreeSmem& S
   } else if (f) {
     for (int i = tid; i < nn; i += nth) {
       S.a[i] = n1_node_diag(*f, t, b0 + i);
-      const int pe = t.t_pedge[b0 + i];
+      const int pe = t.t_pslot[b0 + i];
       const double tg = pe >= 0 ? 1.0 / f->cell_rh[pe] : 0.0;
       S.b[i] = tg;
       t.tg[b0 + i] = tg;  // the top chunk reads the link conductances of its bottom-chunk children
@@ -556,13 +573,14 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
     double dg;
     S.a[i] = n1_node_rhs_diag(f, t, b0 + i, dg);
     S.b[i] = dg;
-    const int pe = t.t_pedge[b0 + i];
+    const int pe = t.t_pslot[b0 + i];
     const double tg = pe >= 0 ? 1.0 / f.cell_rh[pe] : 0.0;
     Se[i] = tg;
     t.tg[b0 + i] = tg;
     S.par[i] = t.t_parent[b0 + i];
   }
   __syncthreads();
+  NXFX_STAMP(top, 3);
   if (top) {  // fold in the bottom-chunk children (written by the other blocks of this launch)
     if (wait_ticket) {
       if (tid == 0) {
@@ -571,6 +589,7 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
       }
       __syncthreads();
     }
+    NXFX_STAMP(top, 4);
     for (int i = tid; i < nn; i += nth) {
       double ad = S.b[i], ar = S.a[i];
       for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
@@ -585,6 +604,7 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
       S.a[i] = ar;
     }
     __syncthreads();
+    NXFX_STAMP(top, 5);
   }
   sweep_up(S, ci, [&](int n) {
     const int i = n - b0;
@@ -601,7 +621,9 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
     S.c[i] = Se[i] * inv;
     S.a[i] = ar;
   });
+  NXFX_STAMP(top, 6);
   for (int i = tid; i < nn; i += nth) { t.d[b0 + i] = S.b[i]; t.gd[b0 + i] = S.c[i]; }
+  NXFX_STAMP(top, 7);
 }
 
 // grid = n_bottom + 1 co-resident blocks (cooperative launch).  The LAST block owns the top chunk: it
@@ -614,16 +636,21 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
   TreeSmem S = tree_view(tree_smem_raw, t.cap);
   double* Se = reinterpret_cast<double*>(tree_smem_raw + ((tree_smem_bytes(t.cap) + 15) & ~(size_t)15));
+  const bool is_top = (int)blockIdx.x == n_bottom;
+  NXFX_STAMP(is_top, 0);
   const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
   load_children(t, ci, S);
+  NXFX_STAMP(is_top, 1);
   // programmatic dependent launch: the schedule tables above are static; everything below reads the
   // output of the preceding kernels.  Dependents (the back-substitution) are released only now, so
   // that whatever they read before their own wait is complete as well.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;");
-  if ((int)blockIdx.x == n_bottom) {
+  NXFX_STAMP(is_top, 2);
+  if (is_top) {
     factor_solve_up(t, S, Se, ci, true, fin, ticket, n_bottom);
     solve_down(t, S, ci);
+    NXFX_STAMP(true, 10);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -631,6 +658,7 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
       __threadfence();
       atomicExch(flag, epoch);
     }
+    NXFX_STAMP(true, 11);
     return;
   }
   factor_solve_up(t, S, Se, ci, false, fin);
@@ -639,13 +667,16 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
     if (S.par[i] < ci.b0 || S.par[i] >= ci.b1) t.r[ci.b0 + i] = S.a[i];
   __threadfence();
   __syncthreads();
+  NXFX_STAMP(false, 8);
   if (threadIdx.x == 0) {
     atomicAdd(ticket, 1u);
     while (atomicAdd(flag, 0u) != epoch) __nanosleep(64);
     __threadfence();
   }
   __syncthreads();
+  NXFX_STAMP(false, 9);
   solve_down(t, S, ci);
+  NXFX_STAMP(false, 10);
 }
 
 // Multi-GPU form of the fused factor + first solve: bottom chunks only (no top chunk, no backward
@@ -675,7 +706,7 @@ tree_top_fs_kernel(TreeDev t, int top_chunk, double* buf, FusedN1 fin) {
   load_children(t, ci, S);
   if (PHASE == kPartial) {
     for (int i = tid; i < nn; i += nth) {
-      const int pe = t.t_pedge[b0 + i];
+      const int pe = t.t_pslot[b0 + i];
       S.a[i] = n1_node_rhs(fin, t, b0 + i);
       S.b[i] = n1_node_diag(fin, t, b0 + i);
       Se[i] = pe >= 0 ? 1.0 / fin.cell_rh[pe] : 0.0;
@@ -817,10 +848,10 @@ bif_diag_n1_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n_bif) return;
   double s = 0.0;
-  for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) s += 1.0 / cell_rh[g.bif_inc[k] >> 1];
+  for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) s += 1.0 / cell_rh[g.edge_slot[g.bif_inc[k] >> 1]];
   const int n = t.t_of_bif[i];
   t.diag0[n] = s;
-  const int pe = t.t_pedge[n];
+  const int pe = t.t_pslot[n];
   t.tg[n] = pe >= 0 ? 1.0 / cell_rh[pe] : 0.0;
 }
 
@@ -832,8 +863,9 @@ bif_rhs_n1_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* 
   double s = lam_weight ? -lam_weight[i] * r[g.loff + i] : -r[g.loff + i];
   for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) {
     const int inc = g.bif_inc[k], e = inc >> 1;
-    const double2 rq = *reinterpret_cast<const double2*>(r + 2 * (size_t)g.edge_slot[e]);
-    const double rp = r[g.poff + e], rh = cell_rh[e];
+    const int slot = g.edge_slot[e];
+    const double2 rq = *reinterpret_cast<const double2*>(r + 2 * (size_t)slot);
+    const double rp = r[g.poff + e], rh = cell_rh[slot];
     const double gc = ((rq.x + rq.y) - 0.5 * rh * rp) / rh;
     s += (inc & 1) ? (rp + gc) : -gc;
   }
@@ -855,12 +887,14 @@ edge_backsub_n1_kernel(Net g, TreeDev t, const double* __restrict__ cell_rh, con
     return;
   }
   // as a programmatic dependent of the tree kernel: r and cell_rh are older than that kernel
-  // (it releases its dependents only after its own wait), the multipliers are its output
-  const int e = idx;
-  const int slot = g.edge_slot[e];
+  // (it releases its dependents only after its own wait), the multipliers are its output.
+  // Thread <-> flux SLOT: the slot record, the flux pair of r / z and cell_rh are contiguous accesses;
+  // only the pressure entry (cell order) is indexed through slot_edge.
+  const int slot = idx;
   const int4 uv = g.slot_uvl[slot];
+  const int e = g.slot_edge[slot];
   const double2 rq = *reinterpret_cast<const double2*>(r + 2 * (size_t)slot);
-  const double rp = r[g.poff + e], rh = cell_rh[e];
+  const double rp = r[g.poff + e], rh = cell_rh[slot];
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const double lu = uv.z >= 0 ? t.lam_nat[uv.z] : 0.0;
   const double lv = uv.w >= 0 ? t.lam_nat[uv.w] : 0.0;

@@ -391,6 +391,16 @@ scale_by_inv_norm_kernel(int n, const double* __restrict__ x, const double* norm
     y[i] = x[i] * s;
 }
 
+// out = (or +=) in with the entries from `off` on multiplied by s (constraint rows of a k-fold accumulated matrix)
+template <bool ADD>
+__global__ void __launch_bounds__(kThreads)
+scale_tail_kernel(int n, int off, double s, const double* __restrict__ in, double* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double v = i < off ? in[i] : in[i] * s;
+    if (ADD) out[i] += v; else out[i] = v;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 add_kernel(int n, const double* __restrict__ z, double* __restrict__ x) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)

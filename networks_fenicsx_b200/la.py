@@ -8,6 +8,7 @@ If petsc4py is importable, ``Mat.to_petsc()`` / ``Vec.to_petsc()`` hand over rea
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -153,7 +154,10 @@ class Vec:
 
 
 class Mat:
-    """Monolithic CSR matrix owned by the device context (pattern from ``nxfx_symbolic``).
+    """Monolithic CSR matrix on the pattern of the device context (``nxfx_symbolic``).  Every ``Mat``
+    owns its value array (``nxfx_matrix_create``) -- the reference hands out independent PETSc
+    matrices (solver.py:43, assembly.py:354), so two solvers / assemblers on one network never alias --
+    and binds it before every operation that reads or writes it.
 
     ``kind`` only changes the reported type and enables ``getNestSubMatrix`` (PETSc MATNEST,
     assembly.py:357); storage is always one CSR so that the SpMV streams a single value array."""
@@ -164,15 +168,32 @@ class Mat:
         self.nnz = int(nnz)
         self.block_sizes = list(block_sizes)
         self.kind = kind
+        mid = C.c_int64()
+        dev.call("nxfx_matrix_create", C.byref(mid))
+        self.mat_id = int(mid.value)
+        self._finalizer = weakref.finalize(self, dev.lib.nxfx_matrix_destroy, dev.handle, C.c_int64(self.mat_id))
+        self.bind()
         rp, ci, va = C.c_void_p(), C.c_void_p(), C.c_void_p()
         dev.call("nxfx_csr_device", C.byref(rp), C.byref(ci), C.byref(va))
         self.rowptr = DeviceArray(dev, self.n + 1, np.int32, ptr=rp.value)
         self.colidx = DeviceArray(dev, self.nnz, np.int32, ptr=ci.value)
         self.values = DeviceArray(dev, self.nnz, np.float64, ptr=va.value)
-        self._zero_pending = True  # values were zeroed by the symbolic phase
+        self._zero_pending = True  # a new matrix is zero
         self._pattern_host = None
         self._prefix = ""
         self.assembled = False
+
+    def bind(self) -> None:
+        """Make this matrix the target / operator of the following device calls."""
+        self.dev.call("nxfx_matrix_bind", C.c_int64(self.mat_id))
+
+    @property
+    def accumulated(self) -> int:
+        """Number of assemblies summed into the matrix since it was last zeroed (ADD_VALUES)."""
+        self.bind()
+        k = C.c_int32()
+        self.dev.call("nxfx_matrix_info", None, None, C.byref(k))
+        return int(k.value)
 
     def getSize(self):
         return (self.n, self.n)
@@ -195,9 +216,15 @@ class Mat:
         self._zero_pending = False
         return z
 
+    def zero_now(self) -> None:
+        """Write the zeros (values and the solver's per-cell data) and forget the accumulated assemblies."""
+        self.bind()
+        self.dev.call("nxfx_matrix_zero")
+        self.assembled = False
+
     def _materialise_zero(self) -> None:
         if self._zero_pending and self.assembled:
-            self.values.zero()
+            self.zero_now()
 
     def assemble(self) -> None:
         return None
@@ -224,6 +251,7 @@ class Mat:
         rp, ci = self.pattern()
         if self._zero_pending:
             return rp, ci, np.zeros(self.nnz)
+        self.dev.sync()
         return rp, ci, self.values.download()
 
     def to_scipy(self):
@@ -240,6 +268,7 @@ class Mat:
     def mult(self, x: Vec, y: Vec) -> None:
         """y = A x on the device (CSR-stream SpMV kernel)."""
         self._materialise_zero()
+        self.bind()
         self.dev.call("nxfx_spmv", x.device_ptr(), y.device_ptr_overwrite())
         y.mark_device_modified()
 

@@ -201,6 +201,7 @@ class Solver:
         opts = self.solve_options()
         self.info = _lib.SolveInfo()
         self._A._materialise_zero()
+        self._A.bind()
         try:
             dev.call(
                 "nxfx_solve", self._b.device_ptr(), self._x.device_ptr_overwrite(),

@@ -61,9 +61,33 @@ def random_tree(n_nodes: int, seed: int, dim: int = 3):
     return G
 
 
-def oracle_for(nm, N):
-    """OracleNetwork on the same arrays the product mesh was built from."""
-    return rp.OracleNetwork(nm._node_pos, nm.graph_edges, nm.edge_colors, N)
+def oracle_for(nm, N, G=None, strategy=None):
+    """OracleNetwork for the network ``nm`` was built from.
+
+    With the original graph ``G`` the oracle does its OWN graph analysis (node / edge order, colouring
+    call of mesh.py:29-42 through ``color_graph_literal``), so that edge ordering or colouring bugs of
+    the product cannot cancel out; it then only checks that both agree.  Without ``G`` (or for graphs
+    beyond the size networkx colours in reasonable time) it falls back to the product's arrays."""
+    from networks_fenicsx_b200.network_generation import ArrayGraph
+
+    if G is None:
+        return rp.OracleNetwork(nm._node_pos, nm.graph_edges, nm.edge_colors, N)
+    graph = G.to_networkx() if isinstance(G, ArrayGraph) else G
+    if graph.number_of_edges() > 20000:
+        return rp.OracleNetwork(nm._node_pos, nm.graph_edges, nm.edge_colors, N)
+    coloring = rp.color_graph_literal(graph, strategy)
+    if isinstance(G, ArrayGraph):  # the arrays ARE the input: their order stands, only the colouring is redone
+        pos, edges = np.asarray(G.pos, dtype=np.float64), np.asarray(G.edges, dtype=np.int64)
+        if strategy is None:
+            colors = np.arange(edges.shape[0], dtype=np.int32)
+        else:
+            colors = np.asarray([rp.lookup_color(coloring, int(u), int(v)) for u, v in edges], dtype=np.int32)
+    else:
+        pos, edges, colors = rp.graph_to_arrays(graph, coloring)
+    assert np.array_equal(edges, nm.graph_edges), "edge order differs from graph.edges()"
+    assert np.array_equal(colors, nm.edge_colors), "edge colouring differs from the reference's call"
+    assert np.array_equal(pos, nm._node_pos)
+    return rp.OracleNetwork(pos, edges, colors, N)
 
 
 def rel_l2(a, b):

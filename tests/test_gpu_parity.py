@@ -26,7 +26,7 @@ def run_case(G, N, strategy, p_bc, R=None, f=None, kind=None, petsc_options=None
     solver = nxfx.Solver(asm, kind=kind, petsc_options=petsc_options)
     solver.assemble()
     sol = solver.solve()
-    net = helpers.oracle_for(nm, N)
+    net = helpers.oracle_for(nm, N, G, strategy)
     A, b = net.assemble(net.eval_pbc(p_bc), R=1.0 if R is None else R, f=0.0 if f is None else f)
     return nm, asm, solver, sol, net, A, b
 
@@ -477,3 +477,114 @@ def test_top_chunk_with_many_child_links():
     A, b = net.assemble(net.eval_pbc(P_Y))
     check_solution(sol, net, A, b)
     assert solver.info.residual_norm <= 1e-12 * solver.info.rhs_norm
+
+
+# ---- matrices are independent objects; the factorisation follows the matrix -----------
+def _x_of(sol):
+    return np.concatenate([f.x.array for f in sol])
+
+
+@pytest.mark.parametrize("N", [1, 3])
+def test_solve_of_accumulated_matrix(N):
+    """ADD_VALUES without zeroEntries (assembly.py:355,362): after a second assemble(A, b) the matrix
+    is 2 A0 -- the solver must factorise THAT matrix, not the element data of one assembly."""
+    G = ng.make_tree(7, 3, 4)
+    rng = np.random.default_rng(11)
+    nc = N * G.number_of_edges()
+    R1, R2 = rng.uniform(0.5, 2.0, nc), rng.uniform(0.1, 3.0, nc)
+    nm = nxfx.NetworkMesh(G, N=N, color_strategy="smallest_last")
+    asm = nxfx.HydraulicNetworkAssembler(nm)
+    asm.compute_forms(p_bc_ex=P_Y, R=R1)
+    opts = {"ksp_type": "preonly", "pc_type": "lu", "ksp_error_if_not_converged": True, "nxfx_final_residual": True}
+    solver = nxfx.Solver(asm, petsc_options=opts)
+    solver.assemble()
+    x0 = _x_of(solver.solve()).copy()
+    net = helpers.oracle_for(nm, N, G, "smallest_last")
+    A1, b1 = net.assemble(net.eval_pbc(P_Y), R=R1)
+    assert helpers.rel_l2(x0, net.solve(A1, b1)) < 1e-10
+    # (i) the same system twice: 2 A0 x = 2 b0
+    asm.assemble(solver.A, solver.b)
+    assert solver.A.accumulated == 2
+    assert np.array_equal(solver.A.getValuesCSR()[2], 2 * A1.data)
+    x = _x_of(solver.solve())
+    assert solver.info.residual_norm <= 1e-12 * solver.info.rhs_norm
+    assert helpers.rel_l2(x, x0) < 1e-10
+    # (ii) a third assembly with ANOTHER resistance: A = 2 A(R1) + A(R2), b = 3 b0
+    asm.compute_forms(p_bc_ex=P_Y, R=R2)
+    asm.assemble(solver.A, solver.b)
+    A2, _ = net.assemble(net.eval_pbc(P_Y), R=R2)
+    Asum = (2 * A1 + A2).tocsr()
+    x = _x_of(solver.solve())
+    assert solver.info.residual_norm <= 1e-12 * solver.info.rhs_norm
+    assert helpers.rel_l2(x, net.solve(Asum, 3 * b1)) < 1e-9
+    # (iii) GMRES on the accumulated matrix with the rescaled Schur preconditioner: exact => 1-2 iterations
+    s2 = nxfx.Solver(asm, petsc_options={"ksp_type": "gmres", "pc_type": "lu", "ksp_rtol": 1e-12})
+    s2.assemble()
+    asm.assemble(s2.A, s2.b)
+    x = _x_of(s2.solve())
+    assert s2.ksp.getIterationNumber() <= 3
+    assert helpers.rel_l2(x, net.solve(A2, b1)) < 1e-9
+
+
+def test_rhs_only_reassembly_keeps_factorisation_of_the_matrix():
+    """compute_forms(R=new) + assemble(assemble_lhs=False): A still holds the OLD resistance and the
+    solve must use it (the factorisation is built from data written with the matrix)."""
+    G = ng.make_tree(8, 3, 4)
+    for N in (1, 2):
+        nm = nxfx.NetworkMesh(G, N=N, color_strategy="smallest_last")
+        asm = nxfx.HydraulicNetworkAssembler(nm)
+        asm.compute_forms(p_bc_ex=P_Y, R=2.0)
+        solver = nxfx.Solver(asm, petsc_options={"ksp_type": "preonly", "pc_type": "lu", "nxfx_final_residual": True,
+                                                 "ksp_error_if_not_converged": True})
+        solver.assemble()
+        x_old = _x_of(solver.solve()).copy()
+        asm.compute_forms(p_bc_ex=lambda x: 2.0 * x[1], R=7.0)
+        solver.assemble(lhs=False, rhs=True)  # new rhs (p_bc doubled), matrix untouched
+        x = _x_of(solver.solve())
+        assert solver.info.residual_norm <= 1e-12 * solver.info.rhs_norm
+        assert solver.ksp.getIterationNumber() == 1, "the stale-factorisation repair path was taken"
+        assert helpers.rel_l2(x, 2.0 * x_old) < 1e-10
+        solver.assemble()  # now the matrix follows: q ~ p_bc / R
+        x_new = _x_of(solver.solve())
+        nq = sum(asm.block_sizes[:-2])
+        assert helpers.rel_l2(x_new[:nq], x_old[:nq] * 2.0 * 2.0 / 7.0) < 1e-10
+
+
+def test_two_assemblers_and_solvers_on_one_network_do_not_alias():
+    """Parameter study on ONE NetworkMesh: independent matrices, boundary data and solutions
+    (the reference returns independent PETSc objects)."""
+    G = ng.make_tree(6, 2, 3)
+    nm = nxfx.NetworkMesh(G, N=2, color_strategy="smallest_last")
+    net = helpers.oracle_for(nm, 2, G, "smallest_last")
+    asm1 = nxfx.HydraulicNetworkAssembler(nm)
+    asm2 = nxfx.HydraulicNetworkAssembler(nm)
+    asm1.compute_forms(p_bc_ex=P_Y, R=1.0)
+    asm2.compute_forms(p_bc_ex=P_X, R=5.0)
+    s1, s2 = nxfx.Solver(asm1), nxfx.Solver(asm2)
+    s1.assemble()
+    s2.assemble()
+    A1, b1 = net.assemble(net.eval_pbc(P_Y), R=1.0)
+    A2, b2 = net.assemble(net.eval_pbc(P_X), R=5.0)
+    assert np.array_equal(s1.A.getValuesCSR()[2], A1.data) and np.array_equal(s1.b.array_r, b1)
+    assert np.array_equal(s2.A.getValuesCSR()[2], A2.data) and np.array_equal(s2.b.array_r, b2)
+    x1 = _x_of(s1.solve())  # s2 was assembled last: s1 must still solve ITS system
+    x2 = _x_of(s2.solve())
+    x1b = _x_of(s1.solve())  # and again after the factors were rebuilt for the other matrix
+    assert helpers.rel_l2(x1, net.solve(A1, b1)) < 1e-10
+    assert helpers.rel_l2(x2, net.solve(A2, b2)) < 1e-10
+    assert helpers.rel_l2(x1b, x1) < 1e-14
+    # a matrix returned by assemble() is a third independent object; a fresh one multiplies as zero
+    A3, b3 = asm1.assemble()
+    assert np.array_equal(A3.getValuesCSR()[2], A1.data) and np.array_equal(s2.A.getValuesCSR()[2], A2.data)
+    xv, yv = s1.x.duplicate(), s1.x.duplicate()
+    xv.array[:] = 1.0
+    fresh = asm1.create_matrix()
+    fresh.mult(xv, yv)
+    assert not yv.array_r.any()
+    A3.mult(xv, yv)
+    assert np.array_equal(yv.array_r, A1 @ np.ones(net.n_dofs))
+    # an assembler with other polynomial degrees needs its own NetworkMesh (one pattern per context)
+    asm_ho = nxfx.HydraulicNetworkAssembler(nm, flux_degree=2, pressure_degree=1)
+    asm_ho.compute_forms(p_bc_ex=P_Y)
+    with pytest.raises(RuntimeError, match="second NetworkMesh"):
+        nxfx.Solver(asm_ho)
