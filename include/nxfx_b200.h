@@ -42,7 +42,8 @@ typedef enum {
   NXFX_ERR_CUDA = -2,          /* CUDA runtime error */
   NXFX_ERR_NOT_CONVERGED = -3, /* mirrors ksp_error_if_not_converged=True, solver.py:64 */
   NXFX_ERR_NCCL = -4,
-  NXFX_ERR_UNSUPPORTED = -5
+  NXFX_ERR_UNSUPPORTED = -5,
+  NXFX_ERR_COMM = -6           /* peer exchange: a rank could not be mapped / did not arrive */
 } nxfx_status;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -248,6 +249,23 @@ int nxfx_assemble_generic(nxfx_ctx* ctx, const double* R_cell_d, double R_const,
  *                        ||b||^2], identical on every rank                                    */
 int nxfx_set_shared(nxfx_ctx* ctx, int32_t n_shared, const int32_t* shared_lm_h,
                     const double* lam_weight_h);
+/* Peer exchange over NVLink: with a communicator the library does the small SUM all-reduces itself.
+ * The kernel that produces the partial sums (the top-chunk block of the fused factor+solve kernel,
+ * the last block of the residual kernel) stores them into every rank's exchange buffer (cudaIpc-
+ * mapped peer memory), raises a flag, waits for the other ranks and adds the contributions in rank
+ * order.  nxfx_solve (ksp preonly, pc lu, one cell per edge) then runs the single-GPU launch
+ * sequence -- assembly, ONE cooperative tree kernel, back-substitution, residual -- with no host
+ * round trip and no NCCL call, and returns norms that are identical on every rank.  All ranks
+ * must call nxfx_solve collectively.
+ *   nxfx_comm_create   after nxfx_set_tree_schedule + nxfx_set_shared: allocates this rank's buffer,
+ *                      handle_out_h receives NXFX_COMM_HANDLE_BYTES (a cudaIpcMemHandle_t)
+ *   (the caller all-gathers the handles with whatever it has: torch.distributed, MPI, a file)
+ *   nxfx_comm_connect  handles_all_h = nranks handles in rank order; maps the peers' buffers     */
+#define NXFX_COMM_HANDLE_BYTES 64
+int nxfx_comm_create(nxfx_ctx* ctx, int32_t rank, int32_t nranks, void* handle_out_h,
+                     int32_t* slot_doubles);
+int nxfx_comm_connect(nxfx_ctx* ctx, const void* handles_all_h);
+int nxfx_comm_destroy(nxfx_ctx* ctx);
 int nxfx_top_size(nxfx_ctx* ctx, int32_t* n_top);
 int nxfx_pc_setup_begin(nxfx_ctx* ctx, double* buf_d);
 int nxfx_pc_setup_end(nxfx_ctx* ctx, double* buf_d);

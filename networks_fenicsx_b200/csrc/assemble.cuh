@@ -344,6 +344,11 @@ constexpr int kLamRows = 256;
 #define NXFX_ST2(ptr, v) __stcs((ptr), (v))
 #define NXFX_ST1(ptr, v) __stcs((ptr), (v))
 #define NXFX_LDS(ptr) __ldcs(ptr)
+// (measured, round 2: writing the right-hand side and R*h with the default policy so that the solve finds
+// them in L2 made the assembly 2 us slower and the solve no faster -- the 117 MB value stream flushes
+// them anyway -- so they stream too)
+#define NXFX_STB2(ptr, v) __stcs((ptr), (v))
+#define NXFX_STB1(ptr, v) __stcs((ptr), (v))
 
 template <bool ACC>
 __device__ __forceinline__ void store_pair(double* __restrict__ vals, size_t idx, double v0, double v1) {
@@ -427,11 +432,11 @@ __device__ __forceinline__ void flux_tile_n1(const Net& g, const Coef& c, const 
       double2* dst = reinterpret_cast<double2*>(b + r);  // r even
       double2 v = make_double2(b0, b1);
       if (ACC) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
-      NXFX_ST2(dst, v);
+      NXFX_STB2(dst, v);
     }
     if (lhs) {
       // the factorisation is built from cell_rh: it follows the matrix (ADD_VALUES included)
-      if (ACC) c.cell_rh[slot] += m; else NXFX_ST1(c.cell_rh + slot, m);
+      if (ACC) c.cell_rh[slot] += m; else NXFX_STB1(c.cell_rh + slot, m);
       const double m3 = __dmul_rn(m, kThird), m6 = __dmul_rn(m, kSixth);
       const bool ufirst = !hv || (hu && t.z < t.w);
       const int nl = (int)hu + (int)hv;
@@ -508,7 +513,7 @@ __device__ __forceinline__ void pressure_tile(const Net& g, const Coef& c, const
                                     load_vertex(g.x2, vertex_id(g, ce, ct.x, ct.y, j + 1)));
         bv = __dmul_rn(c.f_cell ? c.f_cell[cell] : c.f_const, h);
       }
-      if (ACC) b[r] += bv; else NXFX_ST1(b + r, bv);
+      if (ACC) b[r] += bv; else NXFX_STB1(b + r, bv);
     }
   }
 }
@@ -531,7 +536,7 @@ __device__ __forceinline__ void lambda_tile(const Net& g, const int32_t* __restr
     }
   }
   if (rhs && !ACC)
-    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) NXFX_ST1(b + g.loff + i, 0.0);
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) NXFX_STB1(b + g.loff + i, 0.0);
 }
 
 template <bool ACC, bool N1>

@@ -63,6 +63,20 @@ struct MatState {
   int acc_count = 0;  // number of lhs assemblies accumulated since the last zero (ADD_VALUES)
 };
 
+// Peer exchange of the partitioned solve (peer.cuh): this rank's exchange buffer and the mapped
+// buffers of the other ranks.
+struct PeerComm {
+  bool created = false, ready = false;
+  int rank = 0, nranks = 1;
+  int slot = 0;                 // doubles per (channel, parity, source)
+  void* local = nullptr;        // cudaMalloc'ed, exported by cudaIpcGetMemHandle
+  void* base[16] = {};          // every rank's buffer as mapped into this process (base[rank] == local)
+  unsigned int epoch[2] = {0, 0};
+  int* err_h = nullptr;         // mapped pinned word the kernels set when a peer does not arrive
+  int* err_d = nullptr;
+  DevBuf<double> lam_scratch;   // [n_bif] shared rows of a residual before the exchange
+};
+
 }  // namespace nxfx
 
 struct nxfx_ctx {
@@ -109,6 +123,7 @@ struct nxfx_ctx {
   int32_t n_shared = 0;
   nxfx::DevBuf<int32_t> shared_lm;
   nxfx::DevBuf<double> lam_weight, lam_nonshared;
+  nxfx::PeerComm comm;
   // e2e staging
   nxfx::DevBuf<double> e2e_pbc, e2e_b, e2e_x;
 };

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "assemble.cuh"
 #include "ctx.cuh"
@@ -64,6 +65,19 @@ TreeDev make_tree(nxfx_ctx* c) {
   t.r = s.r.p;
   t.lam = s.lam.p;
   return t;
+}
+
+// descriptor of one use of exchange channel `ch` (advances its epoch); nranks = 0 without a communicator
+PeerDev make_peer(nxfx_ctx* c, int ch) {
+  PeerDev p = {};
+  if (!c->comm.ready) return p;
+  for (int r = 0; r < c->comm.nranks; ++r) p.base[r] = reinterpret_cast<unsigned long long>(c->comm.base[r]);
+  p.rank = c->comm.rank;
+  p.nranks = c->comm.nranks;
+  p.slot = c->comm.slot;
+  p.epoch = ++c->comm.epoch[ch];
+  p.err = c->comm.err_d;
+  return p;
 }
 
 int vec_grid(const nxfx_ctx* c, int64_t n) {
@@ -178,6 +192,30 @@ int do_spmv(nxfx_ctx* ctx, const double* x, double* y) {
 // write the matrix (the blocks prefetch matrix tiles before they wait for it)
 int do_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, double* norm2_d, bool pdl = false) {
   const int ntiles = (int)cdiv(ctx->ndofs, kTileRows);
+  if (ctx->comm.ready) {
+    // partitioned network: the kernel itself exchanges the shared rows and the norm partials with the
+    // other ranks over NVLink; norm2_d receives the GLOBAL [||r||^2, ||b||^2], identical on all ranks
+    NXFX_REQUIRE(ctx, ctx->pipe_ok && ctx->lam_nonshared.p, "the fused partitioned residual needs the pipelined SpMV and nxfx_set_shared");
+    const int grid = std::min(ntiles, ctx->sm_count * kPipeBlocksPerSM);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTileRows);
+    cfg.dynamicSmemBytes = kPipeSmem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    NXFX_CUDA(ctx, cudaLaunchKernelEx(&cfg, spmv_pipe_kernel<3>, (int)ctx->ndofs, ntiles, (const int32_t*)ctx->rowptr.p,
+                                      (const int32_t*)ctx->colidx.p, (const double*)ctx->cur->vals.p,
+                                      (const int32_t*)ctx->tile_base.p, x, r, b, ctx->scal.p, ctx->ticket.p, norm2_d,
+                                      (int)ctx->loff, (const double*)ctx->lam_nonshared.p, (const double*)ctx->lam_weight.p,
+                                      make_peer(ctx, 1), (const int32_t*)ctx->shared_lm.p, (int)ctx->n_shared,
+                                      ctx->comm.lam_scratch.p));
+    ctx->launches++;
+    return NXFX_OK;
+  }
   if (ctx->pipe_ok && !pdl) {
     const int grid = std::min(ntiles, ctx->sm_count * kPipeBlocksPerSM);
     NXFX_LAUNCH(ctx, spmv_pipe_kernel<1>, grid, kTileRows, kPipeSmem, (int)ctx->ndofs, ntiles,
@@ -202,7 +240,8 @@ int do_residual(nxfx_ctx* ctx, const double* b, const double* x, double* r, doub
     NXFX_CUDA(ctx, cudaLaunchKernelEx(&cfg, spmv_pipe_kernel<1>, (int)ctx->ndofs, ntiles, (const int32_t*)ctx->rowptr.p,
                                       (const int32_t*)ctx->colidx.p, (const double*)ctx->cur->vals.p,
                                       (const int32_t*)ctx->tile_base.p, x, r, b, ctx->scal.p, ctx->ticket.p, norm2_d, 0,
-                                      (const double*)nullptr, (const double*)nullptr));
+                                      (const double*)nullptr, (const double*)nullptr, PeerDev{}, (const int32_t*)nullptr, 0,
+                                      (double*)nullptr));
     ctx->launches++;
     return NXFX_OK;
   }
@@ -335,21 +374,22 @@ int do_pc_setup(nxfx_ctx* ctx) {
 // factorisation and first application z = P^{-1} r in one cooperative launch (N == 1, single GPU)
 bool can_fuse_setup(const nxfx_ctx* ctx) {
   return ctx->N == 1 && ctx->tree.set && ctx->tree.fast_ok && ctx->tree.coop_fs_ok && ctx->n_bif > 0 &&
-         ctx->tree.n_chunks > 1 && !ctx->lam_weight.p && ctx->cur->acc_count == 1;
+         ctx->tree.n_chunks > 1 && (!ctx->lam_weight.p || ctx->comm.ready) && ctx->cur->acc_count == 1;
 }
 
-int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z) {
+int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z, bool add = false) {
   NXFX_REQUIRE(ctx, is_assembled(ctx), "assemble the matrix before pc_setup");
   NXFX_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(r) & 15) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0,
                "vectors must be 16-byte aligned");
   auto& s = ctx->tree;
   Net g = make_net(ctx);
   TreeDev t = make_tree(ctx);
-  FusedN1 fin{g, r, ctx->cur->cell_rh.p};
+  FusedN1 fin{g, r, ctx->cur->cell_rh.p, ctx->lam_weight.p};
   unsigned int* tk = ctx->ticket.p + 1;
   unsigned int* fl = ctx->ticket.p + 2;
   unsigned int ep = ++s.epoch;
   int nb = s.n_chunks - 1;
+  PeerDev pc = make_peer(ctx, 0);  // multi-GPU: the top block exchanges its partial sums with the peers
   // both kernels are programmatic dependents of their predecessor: the tree kernel stages its
   // schedule tables while the assembly drains, the back-substitution its edge data while the tree
   // kernel finishes (cooperative + programmatic launch; plain cooperative launch if refused)
@@ -365,12 +405,12 @@ int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ctx->pdl_coop_refused ? 1 : 2;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, tree_factor_solve_coop_kernel, t, nb, tk, fl, ep, fin);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, tree_factor_solve_coop_kernel, t, nb, tk, fl, ep, fin, pc);
   if (le != cudaSuccess && cfg.numAttrs == 2) {
     cudaGetLastError();
     ctx->pdl_coop_refused = true;
     cfg.numAttrs = 1;
-    le = cudaLaunchKernelEx(&cfg, tree_factor_solve_coop_kernel, t, nb, tk, fl, ep, fin);
+    le = cudaLaunchKernelEx(&cfg, tree_factor_solve_coop_kernel, t, nb, tk, fl, ep, fin, pc);
   }
   NXFX_CUDA(ctx, le);
   ctx->launches++;
@@ -382,7 +422,8 @@ int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z) {
   bc.stream = ctx->stream;
   bc.attrs = attr + 1;
   bc.numAttrs = 1;
-  NXFX_CUDA(ctx, cudaLaunchKernelEx(&bc, edge_backsub_n1_kernel<false>, g, t, (const double*)ctx->cur->cell_rh.p, r, z));
+  if (add) NXFX_CUDA(ctx, cudaLaunchKernelEx(&bc, edge_backsub_n1_kernel<true>, g, t, (const double*)ctx->cur->cell_rh.p, r, z));
+  else NXFX_CUDA(ctx, cudaLaunchKernelEx(&bc, edge_backsub_n1_kernel<false>, g, t, (const double*)ctx->cur->cell_rh.p, r, z));
   ctx->launches++;
   return NXFX_OK;
 }
@@ -418,6 +459,13 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
     if ((rc = do_pc_apply(ctx, pc_type, r, tmp, false))) return rc;
     NXFX_LAUNCH(ctx, add_kernel, vec_grid(ctx, n), kThreads, 0, n, tmp, z);
     return NXFX_OK;
+  }
+  if (ctx->comm.ready) {
+    // partitioned network: the stored factors of the top chunk are not kept per rank; re-eliminate with
+    // the fused kernel (same cost as a solve: the sweeps are latency-bound) and exchange over NVLink
+    NXFX_REQUIRE(ctx, pc_type == NXFX_PC_NETWORK_SCHUR && can_fuse_setup(ctx),
+                 "the fused partitioned solve needs one cell per edge, a forest schedule that fits the cooperative kernel and pc_type lu");
+    return do_pc_setup_apply(ctx, r, z, add);
   }
   if (pc_type == NXFX_PC_NONE) {
     NXFX_CUDA(ctx, cudaMemcpyAsync(z, r, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -661,6 +709,7 @@ int nxfx_destroy(nxfx_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->scal_h) cudaFreeHost(ctx->scal_h);
+  nxfx_comm_destroy(ctx);
   release_matrices(ctx);
   delete ctx;
   return NXFX_OK;
@@ -771,6 +820,7 @@ int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gd
       return fail(ctx, NXFX_ERR_INVALID, "bif_inc[%d] out of range", k);
   ctx->has_network = ctx->has_pattern = ctx->has_pbc = ctx->pc_ready = false;
   release_matrices(ctx);
+  nxfx_comm_destroy(ctx);
   ctx->edge_slot_h.assign(edge_slot, edge_slot + E);
   ctx->n_shared = 0;
   ctx->shared_lm.release();
@@ -1129,15 +1179,25 @@ int nxfx_solve(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts*
   if (opts->pc_type == NXFX_PC_NETWORK_SCHUR && ctx->generic)
     return fail(ctx, NXFX_ERR_UNSUPPORTED, "the network Schur preconditioner is implemented for flux P1 / pressure DG0");
   bool fused_setup = false;
+  if (ctx->comm.ready)
+    NXFX_REQUIRE(ctx, can_fuse_setup(ctx) || (ctx->pc_ready && ctx->cur->acc_count == 1),
+                 "the fused partitioned solve needs one cell per edge and a forest schedule that fits the cooperative kernel");
   if (opts->pc_type == NXFX_PC_NETWORK_SCHUR && !ctx->pc_ready) {
     // a fresh matrix and a direct solve: factorise while eliminating the right-hand side
     fused_setup = opts->ksp_type == NXFX_KSP_PREONLY && can_fuse_setup(ctx);
     if (!fused_setup && (rc = do_pc_setup(ctx))) return rc;
   }
+  if (ctx->comm.ready)
+    NXFX_REQUIRE(ctx, opts->ksp_type == NXFX_KSP_PREONLY && opts->pc_type == NXFX_PC_NETWORK_SCHUR,
+                 "the partitioned solve is the direct one (ksp_type preonly, pc_type lu)");
   if (opts->ksp_type == NXFX_KSP_PREONLY) rc = solve_preonly(ctx, b, x, opts, info, fused_setup);
   else if (opts->ksp_type == NXFX_KSP_FGMRES) rc = solve_fgmres(ctx, b, x, opts, info);
   else return fail(ctx, NXFX_ERR_UNSUPPORTED, "unknown ksp_type %d", opts->ksp_type);
   if (rc) return rc;
+  if (ctx->comm.ready && *ctx->comm.err_h) {
+    *ctx->comm.err_h = 0;
+    return fail(ctx, NXFX_ERR_COMM, "a peer rank did not deliver its part of the exchange within 4 s");
+  }
   if (!info->converged && opts->error_if_not_converged)
     return fail(ctx, NXFX_ERR_NOT_CONVERGED, "linear solve did not converge: ||r|| = %.3e, ||b|| = %.3e after %d iterations",
                 info->residual_norm, info->rhs_norm, info->iterations);
@@ -1401,6 +1461,71 @@ int nxfx_pc_setup_apply_end(nxfx_ctx* ctx, const double* r, double* z, double* b
   if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeDown>, nb, kTreeThreads, tree_smem_bytes(s.cap), t, nb, ctx->ticket.p + 1, 0);
   const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
   NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, z);
+  return NXFX_OK;
+}
+
+// ---- peer exchange over NVLink (peer.cuh) ----------------------------------------------------------
+static size_t comm_bytes(const PeerComm& c) {
+  return kPeerHeaderBytes + (size_t)kPeerChannels * 2 * (size_t)c.nranks * (size_t)c.slot * sizeof(double);
+}
+
+int nxfx_comm_destroy(nxfx_ctx* ctx) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  PeerComm& c = ctx->comm;
+  if (!c.created) return NXFX_OK;
+  cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < c.nranks; ++r)
+    if (r != c.rank && c.base[r]) cudaIpcCloseMemHandle(c.base[r]);
+  if (c.local) cudaFree(c.local);
+  if (c.err_h) cudaFreeHost(c.err_h);
+  c.lam_scratch.release();
+  c = PeerComm();
+  cudaGetLastError();
+  return NXFX_OK;
+}
+
+int nxfx_comm_create(nxfx_ctx* ctx, int32_t rank, int32_t nranks, void* handle_out, int32_t* slot_doubles) {
+  if (!ctx || !handle_out) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, nranks >= 2 && nranks <= kMaxPeers && rank >= 0 && rank < nranks, "bad rank / nranks");
+  NXFX_REQUIRE(ctx, ctx->tree.set && ctx->lam_nonshared.p, "call nxfx_set_tree_schedule and nxfx_set_shared first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == NXFX_COMM_HANDLE_BYTES, "handle size");
+  nxfx_comm_destroy(ctx);
+  PeerComm& c = ctx->comm;
+  c.rank = rank;
+  c.nranks = nranks;
+  c.slot = (std::max(3 * std::max(ctx->tree.n_top, 1), ctx->n_shared + 2) + 1) & ~1;
+  NXFX_CUDA(ctx, cudaMalloc(&c.local, comm_bytes(c)));
+  NXFX_CUDA(ctx, cudaMemset(c.local, 0, comm_bytes(c)));
+  NXFX_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&c.err_h), sizeof(int), cudaHostAllocMapped));
+  *c.err_h = 0;
+  NXFX_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&c.err_d), c.err_h, 0));
+  NXFX_CUDA(ctx, c.lam_scratch.alloc((size_t)std::max(ctx->n_bif, 1)));
+  NXFX_CUDA(ctx, cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  NXFX_CUDA(ctx, cudaIpcGetMemHandle(&h, c.local));
+  std::memcpy(handle_out, &h, sizeof h);
+  if (slot_doubles) *slot_doubles = c.slot;
+  c.created = true;
+  return NXFX_OK;
+}
+
+int nxfx_comm_connect(nxfx_ctx* ctx, const void* handles_all) {
+  if (!ctx || !handles_all) return NXFX_ERR_INVALID;
+  PeerComm& c = ctx->comm;
+  NXFX_REQUIRE(ctx, c.created && !c.ready, "nxfx_comm_create has not been called (or the communicator is already connected)");
+  const char* hs = static_cast<const char*>(handles_all);
+  for (int r = 0; r < c.nranks; ++r) {
+    if (r == c.rank) { c.base[r] = c.local; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, hs + (size_t)r * sizeof h, sizeof h);
+    cudaError_t e = cudaIpcOpenMemHandle(&c.base[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      c.base[r] = nullptr;
+      return fail(ctx, NXFX_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
+    }
+  }
+  c.ready = true;
   return NXFX_OK;
 }
 

@@ -17,6 +17,7 @@
 #pragma once
 
 #include "assemble.cuh"
+#include "peer.cuh"
 #include "spmv.cuh"
 
 namespace nxfx {
@@ -71,41 +72,86 @@ __device__ __forceinline__ void tree_stamp(bool top, int k) {
 #endif
 
 // n = node in schedule order; its incidences come from the schedule-ordered table (two dependent
-// loads instead of the five of bif_of_t -> bif_ptr -> bif_inc -> edge_slot -> r)
-__device__ __forceinline__ double n1_node_rhs(const FusedN1& f, const TreeDev& t, int n) {
-  const int bi = t.bif_of_t[n];
-  double s = f.lam_weight ? -f.lam_weight[bi] * f.r[f.g.loff + bi] : -f.r[f.g.loff + bi];
-  for (int k = t.t_inc_ptr[n]; k < t.t_inc_ptr[n + 1]; ++k) {
-    const int2 inc = t.t_inc[k];
-    const double2 rq = *reinterpret_cast<const double2*>(f.r + (inc.x & ~1));
-    const double rp = f.r[f.g.poff + inc.y], rh = f.cell_rh[inc.x >> 1];
-    const double gc = ((rq.x + rq.y) - 0.5 * rh * rp) / rh;
-    s += (inc.x & 1) ? (rp + gc) : -gc;
+// loads instead of the five of bif_of_t -> bif_ptr -> bif_inc -> edge_slot -> r).
+// Per incidence (graph edge e in flux slot s, conductance g = 1 / (R h)):
+//   condensed edge flux  gc = g (r_q0 + r_q1) - r_p / 2      [= ((r_q0 + r_q1) - (R h / 2) r_p) / (R h)]
+//   rhs += r_p + gc (in-edge) | -gc (out-edge),   diag += g
+// ONE division per incidence (FP64 divisions are ~30 dependent instructions; they were a third of the
+// staging time), and the incidences are taken two at a time so that their gathers are in flight together.
+// The sums run in incidence order: deterministic, identical in every kernel that stages a node.
+struct IncTerm {
+  double s, g;
+};
+__device__ __forceinline__ IncTerm n1_inc_term(const double* __restrict__ r, const double* __restrict__ cell_rh,
+                                               int poff, int2 inc, double2 rq, double rp, double rh) {
+  const double g = 1.0 / rh;
+  const double gc = g * (rq.x + rq.y) - 0.5 * rp;
+  return IncTerm{(inc.x & 1) ? (rp + gc) : -gc, g};
+}
+
+template <bool RHS, bool DIAG>
+__device__ __forceinline__ void n1_node_eval(const FusedN1& f, const TreeDev& t, int n, double& s_out, double& d_out) {
+  const double* __restrict__ r = f.r;
+  const double* __restrict__ crh = f.cell_rh;
+  const int2* __restrict__ tinc = t.t_inc;
+  const int poff = f.g.poff;
+  const int k0 = t.t_inc_ptr[n], k1 = t.t_inc_ptr[n + 1];
+  double s = 0.0, d = 0.0;
+  if (RHS) {
+    const int bi = t.bif_of_t[n];
+    s = f.lam_weight ? -f.lam_weight[bi] * r[f.g.loff + bi] : -r[f.g.loff + bi];
   }
+  int k = k0;
+  for (; k + 2 <= k1; k += 2) {
+    const int2 i0 = tinc[k], i1 = tinc[k + 1];
+    const double h0 = crh[i0.x >> 1], h1 = crh[i1.x >> 1];
+    if (RHS) {
+      const double2 q0 = *reinterpret_cast<const double2*>(r + (i0.x & ~1));
+      const double2 q1 = *reinterpret_cast<const double2*>(r + (i1.x & ~1));
+      const double p0 = r[poff + i0.y], p1 = r[poff + i1.y];
+      const IncTerm a = n1_inc_term(r, crh, poff, i0, q0, p0, h0);
+      const IncTerm b = n1_inc_term(r, crh, poff, i1, q1, p1, h1);
+      s += a.s;
+      s += b.s;
+      if (DIAG) { d += a.g; d += b.g; }
+    } else {
+      d += 1.0 / h0;
+      d += 1.0 / h1;
+    }
+  }
+  if (k < k1) {
+    const int2 i0 = tinc[k];
+    const double h0 = crh[i0.x >> 1];
+    if (RHS) {
+      const double2 q0 = *reinterpret_cast<const double2*>(r + (i0.x & ~1));
+      const IncTerm a = n1_inc_term(r, crh, poff, i0, q0, r[poff + i0.y], h0);
+      s += a.s;
+      if (DIAG) d += a.g;
+    } else {
+      d += 1.0 / h0;
+    }
+  }
+  s_out = s;
+  d_out = d;
+}
+
+__device__ __forceinline__ double n1_node_rhs(const FusedN1& f, const TreeDev& t, int n) {
+  double s, d;
+  n1_node_eval<true, false>(f, t, n, s, d);
   return s;
 }
 
-// both at once (one pass over the incidences; same operations in the same order as the two above)
+// both at once (one pass over the incidences; same operations in the same order as the two others)
 __device__ __forceinline__ double n1_node_rhs_diag(const FusedN1& f, const TreeDev& t, int n, double& diag) {
-  const int bi = t.bif_of_t[n];
-  double s = f.lam_weight ? -f.lam_weight[bi] * f.r[f.g.loff + bi] : -f.r[f.g.loff + bi];
-  double d = 0.0;
-  for (int k = t.t_inc_ptr[n]; k < t.t_inc_ptr[n + 1]; ++k) {
-    const int2 inc = t.t_inc[k];
-    const double2 rq = *reinterpret_cast<const double2*>(f.r + (inc.x & ~1));
-    const double rp = f.r[f.g.poff + inc.y], rh = f.cell_rh[inc.x >> 1];
-    const double gc = ((rq.x + rq.y) - 0.5 * rh * rp) / rh;
-    s += (inc.x & 1) ? (rp + gc) : -gc;
-    d += 1.0 / rh;
-  }
-  diag = d;
+  double s;
+  n1_node_eval<true, true>(f, t, n, s, diag);
   return s;
 }
 
 __device__ __forceinline__ double n1_node_diag(const FusedN1& f, const TreeDev& t, int n) {
-  double s = 0.0;
-  for (int k = t.t_inc_ptr[n]; k < t.t_inc_ptr[n + 1]; ++k) s += 1.0 / f.cell_rh[t.t_inc[k].x >> 1];
-  return s;
+  double s, d;
+  n1_node_eval<false, true>(f, t, n, s, d);
+  return d;
 }
 
 // schedule-ordered incidence table (built once per schedule)
@@ -321,6 +367,7 @@ __device__ __forceinline__ void factor_chunk(const TreeDev& t, const TreeSmem& S
   const ChunkInfo ci = load_chunk_info(t, chunk, S);
   const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
   load_children(t, ci, S);
+  for (int i = tid; i < nn; i += nth) S.par[i] = t.t_parent[b0 + i];
   if (phase == kFinish) {
     for (int i = tid; i < nn; i += nth) { S.a[i] = buf[i]; S.b[i] = buf[nn + i]; }
   } else if (f) {
@@ -329,7 +376,9 @@ __device__ __forceinline__ void factor_chunk(const TreeDev& t, const TreeSmem& S
       const int pe = t.t_pslot[b0 + i];
       const double tg = pe >= 0 ? 1.0 / f->cell_rh[pe] : 0.0;
       S.b[i] = tg;
-      t.tg[b0 + i] = tg;  // the top chunk reads the link conductances of its bottom-chunk children
+      // the top chunk reads the link conductances of its bottom-chunk children (the chunk roots)
+      const int p = t.t_parent[b0 + i];
+      if (p < b0 || p >= ci.b1) t.tg[b0 + i] = tg;
     }
   } else {
     for (int i = tid; i < nn; i += nth) { S.a[i] = t.diag0[b0 + i]; S.b[i] = t.tg[b0 + i]; }
@@ -412,7 +461,8 @@ __device__ __forceinline__ void solve_up(const TreeDev& t, const TreeSmem& S, co
 }
 
 // lam = r/d + gd * lam(parent); parents outside the chunk (top chunk) are read through L2
-__device__ __forceinline__ void solve_down(const TreeDev& t, const TreeSmem& S, const ChunkInfo& ci) {
+// `top`: only the top chunk's multipliers are read by other chunks (through t.lam, schedule order)
+__device__ __forceinline__ void solve_down(const TreeDev& t, const TreeSmem& S, const ChunkInfo& ci, bool top) {
   const int b0 = ci.b0, b1 = ci.b1, nn = ci.b1 - ci.b0;
   sweep_down(S, ci, [&](int n) {
     const int i = n - b0;
@@ -423,7 +473,7 @@ __device__ __forceinline__ void solve_down(const TreeDev& t, const TreeSmem& S, 
     S.a[i] = v;
   });
   for (int i = threadIdx.x; i < nn; i += blockDim.x) {
-    t.lam[b0 + i] = S.a[i];
+    if (top) t.lam[b0 + i] = S.a[i];
     t.lam_nat[t.bif_of_t[b0 + i]] = S.a[i];
   }
 }
@@ -473,7 +523,7 @@ tree_top_kernel(TreeDev t, int top_chunk, double* buf) {
     load_solve_chunk(t, ti, S);
     __syncthreads();
     solve_up(t, S, ti, true, PHASE, buf);
-    if (PHASE == kFinish) solve_down(t, S, ti);
+    if (PHASE == kFinish) solve_down(t, S, ti, true);
   }
 }
 
@@ -484,9 +534,10 @@ tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top) {
   TreeSmem S = tree_view(tree_smem_raw, t.cap);
   if (MODE == kTreeDown) {
     const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
+    load_children(t, ci, S);
     load_solve_chunk(t, ci, S);
     __syncthreads();
-    solve_down(t, S, ci);
+    solve_down(t, S, ci, false);
     return;
   }
   if (n_bottom > 0) {
@@ -505,7 +556,7 @@ tree_solve_kernel(TreeDev t, int n_bottom, unsigned int* ticket, int do_top) {
   load_solve_chunk(t, ti, S);
   __syncthreads();
   solve_up(t, S, ti, true);
-  solve_down(t, S, ti);
+  solve_down(t, S, ti, true);
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
@@ -530,7 +581,7 @@ tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned i
     }
     __syncthreads();
     solve_up(t, S, ci, true);
-    solve_down(t, S, ci);
+    solve_down(t, S, ci, true);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -551,7 +602,7 @@ tree_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned i
     __threadfence();
   }
   __syncthreads();
-  solve_down(t, S, ci);
+  solve_down(t, S, ci, false);
 }
 
 // ---- factorisation fused with the first solve (N == 1, single GPU) --------------------------------
@@ -565,9 +616,14 @@ __host__ __device__ constexpr size_t tree_smem_bytes_fs(int cap) {
 
 // wait_ticket (top chunk in its own block): the chunk's own values are staged first, then the block
 // waits until all wait_count bottom blocks have published their roots.
+// pc (top chunk, multi-GPU): after this rank's bottom-chunk children are folded in, the partial pivots /
+// link conductances / right-hand sides of the replicated top chunk are exchanged with the other ranks
+// over NVLink (peer_allgather) and added up in rank order; every rank then eliminates the identical
+// top chunk.
 __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem& S, double* __restrict__ Se,
                                                 const ChunkInfo& ci, bool top, const FusedN1& f,
-                                                unsigned int* wait_ticket = nullptr, int wait_count = 0) {
+                                                unsigned int* wait_ticket = nullptr, int wait_count = 0,
+                                                const PeerDev* pc = nullptr) {
   const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
   for (int i = tid; i < nn; i += nth) {
     double dg;
@@ -576,8 +632,9 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
     const int pe = t.t_pslot[b0 + i];
     const double tg = pe >= 0 ? 1.0 / f.cell_rh[pe] : 0.0;
     Se[i] = tg;
-    t.tg[b0 + i] = tg;
-    S.par[i] = t.t_parent[b0 + i];
+    const int p = t.t_parent[b0 + i];
+    S.par[i] = p;
+    if (p < b0 || p >= ci.b1) t.tg[b0 + i] = tg;  // chunk roots: read by the top chunk
   }
   __syncthreads();
   NXFX_STAMP(top, 3);
@@ -605,6 +662,22 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
     }
     __syncthreads();
     NXFX_STAMP(top, 5);
+    if (pc && pc->nranks > 1) {
+      peer_allgather(*pc, 0, 3 * nn, [&](int i) { return i < nn ? S.b[i] : (i < 2 * nn ? Se[i - nn] : S.a[i - 2 * nn]); });
+      for (int i = tid; i < nn; i += nth) {
+        double ad = 0.0, tg = 0.0, ar = 0.0;
+        for (int src = 0; src < pc->nranks; ++src) {
+          const double* d = peer_data(*pc, pc->rank, 0, src);
+          ad += __ldcg(d + i);
+          tg += __ldcg(d + nn + i);
+          ar += __ldcg(d + 2 * nn + i);
+        }
+        S.b[i] = ad;
+        Se[i] = tg;
+        S.a[i] = ar;
+      }
+      __syncthreads();
+    }
   }
   sweep_up(S, ci, [&](int n) {
     const int i = n - b0;
@@ -632,7 +705,7 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
 // then back-substitute their chunk straight from shared memory.
 __global__ void __launch_bounds__(kTreeThreads, 2)
 tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch,
-                              FusedN1 fin) {
+                              FusedN1 fin, PeerDev pc) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
   TreeSmem S = tree_view(tree_smem_raw, t.cap);
   double* Se = reinterpret_cast<double*>(tree_smem_raw + ((tree_smem_bytes(t.cap) + 15) & ~(size_t)15));
@@ -648,8 +721,8 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
   asm volatile("griddepcontrol.launch_dependents;");
   NXFX_STAMP(is_top, 2);
   if (is_top) {
-    factor_solve_up(t, S, Se, ci, true, fin, ticket, n_bottom);
-    solve_down(t, S, ci);
+    factor_solve_up(t, S, Se, ci, true, fin, ticket, n_bottom, &pc);
+    solve_down(t, S, ci, true);
     NXFX_STAMP(true, 10);
     __threadfence();
     __syncthreads();
@@ -675,7 +748,7 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
   }
   __syncthreads();
   NXFX_STAMP(false, 9);
-  solve_down(t, S, ci);
+  solve_down(t, S, ci, false);
   NXFX_STAMP(false, 10);
 }
 
@@ -750,7 +823,7 @@ tree_top_fs_kernel(TreeDev t, int top_chunk, double* buf, FusedN1 fin) {
     S.a[i] = ar;
   });
   for (int i = tid; i < nn; i += nth) { t.d[b0 + i] = S.b[i]; t.gd[b0 + i] = S.c[i]; }
-  solve_down(t, S, ci);
+  solve_down(t, S, ci, true);
   }
 }
 
@@ -866,7 +939,7 @@ bif_rhs_n1_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* 
     const int slot = g.edge_slot[e];
     const double2 rq = *reinterpret_cast<const double2*>(r + 2 * (size_t)slot);
     const double rp = r[g.poff + e], rh = cell_rh[slot];
-    const double gc = ((rq.x + rq.y) - 0.5 * rh * rp) / rh;
+    const double gc = (1.0 / rh) * (rq.x + rq.y) - 0.5 * rp;  // as n1_inc_term
     s += (inc & 1) ? (rp + gc) : -gc;
   }
   t.r[t.t_of_bif[i]] = s;

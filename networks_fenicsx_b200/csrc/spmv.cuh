@@ -11,6 +11,7 @@
 #pragma once
 
 #include "ctx.cuh"
+#include "peer.cuh"
 
 namespace nxfx {
 
@@ -42,7 +43,7 @@ __device__ __forceinline__ double block_sum(double v, double* red /* [THREADS/32
 // Last-block-done final reduction of per-block partials -> out[0..K).  Deterministic: the last
 // block (whichever it is) sums the partials in index order with the same fixed tree.
 template <int THREADS, int K>
-__device__ __forceinline__ void finish_partials(double (&mine)[K], double* partial, int nblocks,
+__device__ __forceinline__ bool finish_partials(double (&mine)[K], double* partial, int nblocks,
                                                 unsigned int* ticket, double* out, double* red) {
   __shared__ bool last;
   if (threadIdx.x == 0) {
@@ -53,7 +54,7 @@ __device__ __forceinline__ void finish_partials(double (&mine)[K], double* parti
     last = (t == (unsigned int)nblocks - 1);
   }
   __syncthreads();
-  if (!last) return;
+  if (!last) return false;
   __threadfence();
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -64,10 +65,14 @@ __device__ __forceinline__ void finish_partials(double (&mine)[K], double* parti
     if (threadIdx.x == 0) out[k] = s;
   }
   if (threadIdx.x == 0) *ticket = 0u;
+  return true;
 }
 
 // MODE 0: y = A x.   MODE 1: y = b - A x and norm2_out[0] = ||y||^2, norm2_out[1] = ||b||^2
 // MODE 2 (pipeline kernel): as 1 with the rows >= loff weighted by w_r / w_b (multi-GPU partial norms)
+// MODE 3 (pipeline kernel): as 2, and the block that finishes last exchanges the shared multiplier rows
+//         of r and the two norm partials with the other ranks over NVLink (peer_allgather), adds them up
+//         in rank order, writes the reduced rows back into y and the GLOBAL norms to norm2_out
 // (block partials, grid-strided tiles so that the partial count stays bounded).
 template <int MODE>
 __global__ void __launch_bounds__(kTileRows)
@@ -206,7 +211,9 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
                  const int32_t* __restrict__ tile_base, const double* __restrict__ x,
                  double* __restrict__ y, const double* __restrict__ b, double* partial,
                  unsigned int* ticket, double* norm2_out, int loff = 0,
-                 const double* __restrict__ w_r = nullptr, const double* __restrict__ w_b = nullptr) {
+                 const double* __restrict__ w_r = nullptr, const double* __restrict__ w_b = nullptr,
+                 PeerDev pc = PeerDev{}, const int32_t* __restrict__ shared_lm = nullptr, int n_shared = 0,
+                 double* lam_scratch = nullptr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SpmvStage* st = reinterpret_cast<SpmvStage*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(SpmvStage));
@@ -292,9 +299,12 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
       } else {
         const double r = __dsub_rn(bi, acc);
         if (y) y[r0 + tid] = r;  // y == nullptr: norms only
-        if (MODE == 2 && r0 + tid >= loff) {  // multi-GPU: weighted multiplier rows
-          nrm += w_r[r0 + tid - loff] * r * r;
+        if (MODE >= 2 && r0 + tid >= loff) {  // multi-GPU: weighted multiplier rows
+          const double wr = w_r[r0 + tid - loff];
+          nrm += wr * r * r;
           nrb += w_b[r0 + tid - loff] * bi * bi;
+          // replicated rows (weight 0 on every rank) hold partial sums: parked for the exchange below
+          if (MODE == 3 && wr == 0.0) lam_scratch[r0 + tid - loff] = r;
         } else {
           nrm += r * r;
           nrb += bi * bi;
@@ -305,9 +315,35 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
   }
-  if (MODE >= 1) {
+  if (MODE >= 1 && MODE < 3) {
     double mine[2] = {block_sum<kTileRows>(nrm, red), block_sum<kTileRows>(nrb, red)};
     finish_partials<kTileRows, 2>(mine, partial, gridDim.x, ticket, norm2_out, red);
+  }
+  if (MODE == 3) {
+    __shared__ double loc[2];
+    double mine[2] = {block_sum<kTileRows>(nrm, red), block_sum<kTileRows>(nrb, red)};
+    if (!finish_partials<kTileRows, 2>(mine, partial, gridDim.x, ticket, loc, red)) return;
+    __syncthreads();  // loc[] written by thread 0
+    peer_allgather(pc, 1, n_shared + 2,
+                   [&](int i) { return i < n_shared ? __ldcg(lam_scratch + shared_lm[i]) : loc[i - n_shared]; });
+    double acc = 0.0;
+    for (int i = tid; i < n_shared; i += kTileRows) {
+      double v = 0.0;
+      for (int src = 0; src < pc.nranks; ++src) v += __ldcg(peer_data(pc, pc.rank, 1, src) + i);
+      if (y) y[loff + shared_lm[i]] = v;
+      acc += v * v;
+    }
+    acc = block_sum<kTileRows>(acc, red);
+    if (tid == 0) {
+      double s0 = acc, s1 = 0.0;
+      for (int src = 0; src < pc.nranks; ++src) {
+        const double* d = peer_data(pc, pc.rank, 1, src);
+        s0 += __ldcg(d + n_shared);
+        s1 += __ldcg(d + n_shared + 1);
+      }
+      norm2_out[0] = s0;
+      norm2_out[1] = s1;
+    }
   }
 }
 

@@ -120,13 +120,18 @@ class DistributedSolver:
     Args:
         graph: the GLOBAL network (every rank passes the same :class:`ArrayGraph`).
         N: cells per graph edge.
-        p_bc_ex, f, R: as :meth:`HydraulicNetworkAssembler.compute_forms` (``R``/``f`` per-cell arrays
-            must already be restricted to the local edges).
+        p_bc_ex, f, R: as :meth:`HydraulicNetworkAssembler.compute_forms`; ``R``/``f`` arrays are given for
+            the GLOBAL network (per graph edge or per cell) and restricted to the local edges here.
+        exchange: ``"peer"``: the kernels exchange the partial sums themselves over NVLink (CUDA IPC peer
+            memory, ``peer.cuh``) -- the single-GPU launch sequence, no NCCL call, one host sync per solve
+            (needs ``N == 1``); ``"nccl"``: split phases around ``torch.distributed`` all-reduces;
+            ``"auto"``: peer when available.
         device: CUDA ordinal of this rank.
     """
 
     def __init__(self, graph: ArrayGraph, N: int, p_bc_ex, f=None, R=None, device: int = 0,
-                 color_strategy="smallest_last", chunk_nodes: int = CHUNK_NODES, group=None):
+                 color_strategy="smallest_last", chunk_nodes: int = CHUNK_NODES, group=None,
+                 exchange: str = "auto"):
         import ctypes as C
 
         import torch
@@ -146,7 +151,7 @@ class DistributedSolver:
         assert np.array_equal(part.global_nodes[self.mesh.bifurcation_values], part.global_nodes[
             np.flatnonzero(part.node_degree > 1)])
         self.assembler = HydraulicNetworkAssembler(self.mesh)
-        self.assembler.compute_forms(p_bc_ex=p_bc_ex, f=f, R=R)
+        self.assembler.compute_forms(p_bc_ex=p_bc_ex, f=self._restrict(f, N, graph), R=self._restrict(R, N, graph))
         self.solver = Solver(self.assembler, schedule=part.schedule)
         self.dev = self.mesh.device
         shared = np.ascontiguousarray(part.shared_lm, dtype=np.int32)
@@ -160,6 +165,63 @@ class DistributedSolver:
         self.n_dofs_global = int(self._allreduce_scalar(self._owned_dofs()))
         self.history: list[float] = []
         self.rhs_norm = float("nan")
+        self.corrections = 0
+        self.exchange = "nccl"
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        if exchange != "nccl" and N == 1:
+            self._connect_peers(required=exchange == "peer")
+        elif exchange == "peer":
+            raise ValueError("exchange='peer' (fused kernels with in-kernel NVLink exchange) needs N == 1")
+
+    def _connect_peers(self, required: bool) -> None:
+        """Peer exchange over NVLink (``peer.cuh``): every rank exports its exchange buffer as a CUDA IPC
+        handle, the handles are all-gathered with torch.distributed (the only use of the process group
+        on this path) and mapped.  All ranks agree on the outcome; any failure falls back to the
+        host-driven NCCL all-reduces unless ``required``."""
+        C, torch, dist = self._C, self._torch, self._dist
+        handle = (C.c_ubyte * 64)()
+        slot = C.c_int32(0)
+        ok = 1
+        try:
+            self.dev.call("nxfx_comm_create", self.rank, self.world, C.cast(handle, C.c_void_p), C.byref(slot))
+        except RuntimeError as exc:  # e.g. the schedule does not fit the cooperative kernel
+            ok, err = 0, str(exc)
+        cuda = self._top.device
+        mine = torch.tensor(list(bytes(handle)) + [slot.value & 0xFF, (slot.value >> 8) & 0xFF, (slot.value >> 16) & 0xFF, ok],
+                            dtype=torch.uint8, device=cuda)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=self._group)
+        table = np.stack([t.cpu().numpy() for t in allh])
+        if ok and table[:, 67].all() and (table[:, 64:67] == table[0, 64:67]).all():
+            blob = np.ascontiguousarray(table[:, :64]).tobytes()
+            try:
+                self.dev.call("nxfx_comm_connect", C.c_char_p(blob))
+            except RuntimeError as exc:
+                ok, err = 0, str(exc)
+        else:
+            ok, err = 0, "a rank could not create its exchange buffer (or the slot sizes differ)"
+        if self._allreduce_scalar(float(ok)) == float(self.world):
+            self.exchange = "peer"
+            dist.barrier(group=self._group)  # every buffer is mapped and zeroed before the first flag is written
+            return
+        self.dev.call("nxfx_comm_destroy")
+        if required:
+            raise RuntimeError(f"peer exchange unavailable: {err if not ok else 'another rank failed'}")
+
+    def _restrict(self, coef, N: int, graph: ArrayGraph):
+        """Per-edge / per-cell coefficient arrays of the GLOBAL network -> this rank's edges (arrays that
+        already have the local size, scalars and None pass through)."""
+        if coef is None or np.isscalar(coef):
+            return coef
+        arr = np.asarray(coef, dtype=np.float64)
+        E = graph.number_of_edges()
+        ge = self.part.global_edges
+        if arr.shape == (E,) and ge.size != E:
+            return arr[ge]
+        if arr.shape == (E * N,) and ge.size != E:
+            return arr.reshape(E, N)[ge].ravel()
+        return arr
 
     def _owned_dofs(self) -> int:
         return int(self.assembler.num_dofs - self.part.n_top + (self.part.n_top if self.rank == 0 else 0))
@@ -190,6 +252,8 @@ class DistributedSolver:
         dev = self.dev
         b = self.solver.b.device_ptr()
         x = self.solver.x.device_ptr_overwrite()
+        if self.exchange == "peer":
+            return self._solve_peer(b, x, refine_steps, final_residual, refine_rtol)
         # factorisation and first application share one all-reduce: the forward sweep of the bottom
         # chunks only needs their own factors
         top = self._ptr(self._top)  # [partial pivots | link conductances | partial rhs], 3 n_top
@@ -214,6 +278,28 @@ class DistributedSolver:
             dev.sync()
         self.solver.x.mark_device_modified()
         self.corrections = applied
+        return self.history
+
+    def _solve_peer(self, b, x, refine_steps, final_residual, refine_rtol):
+        """The single-GPU launch sequence (fused factor+solve tree kernel, back-substitution, residual)
+        with the exchanges done inside the kernels over NVLink: one library call, one host
+        synchronisation, no NCCL."""
+        from . import _lib
+
+        C = self._C
+        opts = self.solver.solve_options()
+        opts.ksp_type, opts.pc_type = _lib.KSP_PREONLY, _lib.PC_NETWORK_SCHUR
+        opts.refine_steps, opts.final_residual, opts.refine_rtol = int(refine_steps), int(bool(final_residual)), float(refine_rtol)
+        opts.error_if_not_converged = 0
+        info = _lib.SolveInfo()
+        self.solver.A._materialise_zero()
+        self.solver.A.bind()
+        self.dev.call("nxfx_solve", b, x, C.byref(opts), C.byref(info))
+        self.solver.x.mark_device_modified()
+        self.rhs_norm = float(info.rhs_norm)
+        den = self.rhs_norm if self.rhs_norm > 0 else 1.0
+        self.history = [info.history[i] / den for i in range(info.history_len)]
+        self.corrections = int(info.iterations) - 1
         return self.history
 
     def _residual(self, b, x, k: int) -> None:
