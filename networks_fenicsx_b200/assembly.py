@@ -188,13 +188,15 @@ class HydraulicNetworkAssembler:
         dev.call("nxfx_set_boundary_pressure", self._pbc_d.c_ptr)  # into the vertex records
         dev.sync()
         nm._pbc_owner = self  # the vertex records now hold THIS assembler's boundary data
-        self._R = self._coefficient(R, 1.0, nc, "R")
-        self._f = self._coefficient(f, 0.0, nc, "f")
+        self._R = self._coefficient(R, 1.0, nc, "R", self._R[0])
+        self._f = self._coefficient(f, 0.0, nc, "f", self._f[0])
         C_ = nm.num_edge_colors
         self._a = _BilinearBlocks(C_)
         self._L = _LinearBlocks(C_)
 
-    def _coefficient(self, val, default, nc, name):
+    def _coefficient(self, val, default, nc, name, previous=None):
+        """``previous``: the device array of the last call -- reused (no allocation, asynchronous upload)
+        when the new coefficient is an array of the same size, e.g. in a time loop."""
         if val is None:
             return (None, float(default))
         if np.isscalar(val) or (hasattr(val, "value") and np.ndim(val.value) == 0):
@@ -205,7 +207,13 @@ class HydraulicNetworkAssembler:
             arr = np.repeat(arr, nm.cells_per_edge)
         if arr.shape != (nc,):
             raise ValueError(f"{name} must be a scalar, one value per cell ({nc}) or per graph edge")
-        return (nm.device.from_host(np.ascontiguousarray(arr)), 0.0)
+        arr = np.ascontiguousarray(arr)
+        if previous is not None and previous.n == arr.size:
+            previous.upload(arr, sync=False)  # ordered on the context's stream before the next assembly
+            self._coef_keepalive = getattr(self, "_coef_keepalive", {})
+            self._coef_keepalive[name] = arr  # the asynchronous copy reads the host array
+            return (previous, 0.0)
+        return (nm.device.from_host(arr), 0.0)
 
     # ---- accessors (assembly.py:301-326, 370-398) -------------------------------------------------
     @property

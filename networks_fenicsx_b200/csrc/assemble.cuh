@@ -55,8 +55,21 @@ struct Net {
   const int32_t* __restrict__ edge_slot;
   const int32_t* __restrict__ bif_ptr;
   const int32_t* __restrict__ bif_inc;
-  const double2* __restrict__ x2;  // [nv] vertex records {x, y | z, p_bc} (32 B each)
+  const double2* __restrict__ x2;  // [nv] vertex records {x, y | z, p_bc or tagged multiplier index} (32 B each)
+  const int2* __restrict__ slot_uv;          // [E] {u, v} in slot order (N == 1 assembly: 8 instead of 16 bytes per edge)
+  const uint32_t* __restrict__ bif_in_bits;  // bit k = incidence k is an in-edge (multiplier rows: 1 bit instead of 4 bytes)
 };
+
+// The 4th double of a vertex record holds the boundary pressure -- only ever read at BOUNDARY vertices
+// (assembly.py:258-260) -- so at bifurcation vertices it carries the node's multiplier index instead, as
+// a tagged NaN: the one-cell-per-edge assembly then finds lm(u), lm(v) in the records it loads anyway.
+constexpr unsigned int kLmTag = 0x7FF8B1F0u;
+__device__ __forceinline__ double lm_box(int lm) {
+  return __hiloint2double((int)kLmTag, lm);
+}
+__device__ __forceinline__ int lm_unbox(double p) {  // multiplier index, or -1 at a boundary / interior vertex
+  return (unsigned int)__double2hiint(p) == kLmTag ? __double2loint(p) : -1;
+}
 
 struct Coef {
   const double* __restrict__ R_cell;  // [nc] or null
@@ -105,7 +118,13 @@ pad_nodes_kernel(int n_nodes, int gdim, const double* __restrict__ pos, double* 
 __global__ void __launch_bounds__(kThreads)
 set_pbc_kernel(int64_t nv, const double* __restrict__ pbc, double* __restrict__ x) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < nv) x[4 * i + 3] = pbc[i];
+  if (i < nv && lm_unbox(x[4 * i + 3]) < 0) x[4 * i + 3] = pbc[i];  // bifurcation records keep their tag
+}
+
+__global__ void __launch_bounds__(kThreads)
+tag_lm_kernel(int n_nodes, const int32_t* __restrict__ node_lm, double* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_nodes && node_lm[i] >= 0) x[4 * (size_t)i + 3] = lm_box(node_lm[i]);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -385,8 +404,9 @@ __device__ __forceinline__ void flush_tile(const double* sm, double* __restrict_
 }
 
 // N == 1 flux tile: thread <-> edge slot, rows 2*slot (vertex u) and 2*slot+1 (vertex v).
-// Everything the thread needs comes from its 16-byte slot record {u, v, lm(u), lm(v)} and the two vertex
-// records: the row's CSR offset inside the tile is 6 * (slots before) + 2 * (multiplier entries before) --
+// Everything the thread needs comes from its 8-byte slot record {u, v} and the two vertex records (which
+// carry the multiplier index of a bifurcation vertex in place of the unused boundary pressure): the row's
+// CSR offset inside the tile is 6 * (slots before) + 2 * (multiplier entries before) --
 // a ballot / popcount prefix over the block instead of a strided rowptr load --, and R*h is stored in SLOT
 // order (coalesced; the graph-edge index is only needed for a per-cell R array).
 template <bool ACC>
@@ -399,7 +419,13 @@ __device__ __forceinline__ void flux_tile_n1(const Net& g, const Coef& c, const 
   const bool active = slot < g.E;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int4 t = make_int4(0, 0, -1, -1);
-  if (active) t = NXFX_LDS(g.slot_uvl + slot);
+  VertexRec v0, v1;
+  if (active) {
+    const int2 uv = NXFX_LDS(g.slot_uv + slot);
+    v0 = load_vertex(g.x2, uv.x);
+    v1 = load_vertex(g.x2, uv.y);
+    t = make_int4(uv.x, uv.y, lm_unbox(v0.p), lm_unbox(v1.p));
+  }
   const bool hu = t.z >= 0, hv = t.w >= 0;
   const unsigned bu = __ballot_sync(0xffffffffu, hu), bv = __ballot_sync(0xffffffffu, hv);
   const unsigned lt = (1u << lane) - 1u;
@@ -407,10 +433,7 @@ __device__ __forceinline__ void flux_tile_n1(const Net& g, const Coef& c, const 
   if (lane == 0) warp_nl[w] = __popc(bu) + __popc(bv);
   const int sbase = rowptr[r0];
   double m = 0.0;
-  VertexRec v0, v1;
   if (active) {
-    v0 = load_vertex(g.x2, t.x);
-    v1 = load_vertex(g.x2, t.y);
     const double R = c.R_cell ? c.R_cell[NXFX_LDS(g.slot_edge + slot)] : c.R_const;
     m = __dmul_rn(R, seg_length(v0, v1));
   }
@@ -531,7 +554,7 @@ __device__ __forceinline__ void lambda_tile(const Net& g, const int32_t* __restr
     const int k0 = g.bif_ptr[i0], k1 = g.bif_ptr[i1];
     const int sbase = rowptr[g.loff + i0];
     for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
-      const bool in = g.bif_inc[k] & 1;
+      const bool in = (g.bif_in_bits[k >> 5] >> (k & 31)) & 1u;
       store_pair<ACC>(vals, (size_t)sbase + 2 * (size_t)(k - k0), in ? 0.0 : -1.0, in ? 1.0 : 0.0);
     }
   }

@@ -95,6 +95,8 @@ struct nxfx_ctx {
   nxfx::DevBuf<double> x;          // [nv][4] vertex records {x, y, z, p_bc} (graph nodes first)
   nxfx::DevBuf<double> pos_stage;  // [n_nodes*gdim] upload staging
   nxfx::DevBuf<int4> slot_uvl;     // [E] {u, v, lm(u), lm(v)} in slot order
+  nxfx::DevBuf<int2> slot_uv;      // [E] {u, v} in slot order (N == 1 assembly)
+  nxfx::DevBuf<uint32_t> bif_in_bits;  // [ceil(n_inc / 32)] in-edge flag of every incidence
   nxfx::DevBuf<int32_t> slot_edge, edge_slot, edge_u, edge_v, bif_ptr, bif_inc;
   // pattern + values
   nxfx::DevBuf<int32_t> rowptr, colidx, tile_base;

@@ -38,6 +38,8 @@ Net make_net(const nxfx_ctx* c) {
   g.bif_ptr = c->bif_ptr.p;
   g.bif_inc = c->bif_inc.p;
   g.x2 = reinterpret_cast<const double2*>(c->x.p);
+  g.slot_uv = c->slot_uv.p;
+  g.bif_in_bits = c->bif_in_bits.p;
   return g;
 }
 
@@ -837,6 +839,15 @@ int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gd
   if ((rc = upload(ctx, ctx->edge_slot, edge_slot, (size_t)E))) return rc;
   if ((rc = upload(ctx, ctx->slot_edge, slot_edge.data(), (size_t)E))) return rc;
   if ((rc = upload(ctx, ctx->slot_uvl, uvl.data(), (size_t)E))) return rc;
+  std::vector<int2> uv((size_t)E);
+  for (int64_t s = 0; s < E; ++s) uv[s] = make_int2(uvl[s].x, uvl[s].y);
+  if ((rc = upload(ctx, ctx->slot_uv, uv.data(), (size_t)E))) return rc;
+  std::vector<uint32_t> in_bits((size_t)(n_inc + 31) / 32 + 1, 0u);
+  for (int32_t k = 0; k < n_inc; ++k)
+    if (bif_inc[k] & 1) in_bits[k >> 5] |= 1u << (k & 31);
+  if ((rc = upload(ctx, ctx->bif_in_bits, in_bits.data(), in_bits.size()))) return rc;
+  DevBuf<int32_t> node_lm_d;
+  if ((rc = upload(ctx, node_lm_d, node_lm, (size_t)n_nodes))) return rc;
   if ((rc = upload(ctx, ctx->bif_ptr, bif_ptr, (size_t)n_bif + 1))) return rc;
   if ((rc = upload(ctx, ctx->bif_inc, bif_inc, (size_t)n_inc))) return rc;
   NXFX_CUDA(ctx, ctx->x.alloc((size_t)nv * 4));
@@ -846,6 +857,8 @@ int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gd
   NXFX_CUDA(ctx, ctx->edge_fn.alloc((size_t)E));
   if ((rc = ensure_scal(ctx))) return rc;
   if ((rc = build_vertices(ctx))) return rc;
+  // bifurcation vertices carry their multiplier index in the (there unused) boundary-pressure slot
+  NXFX_LAUNCH(ctx, tag_lm_kernel, (int)cdiv(n_nodes, kThreads), kThreads, 0, n_nodes, node_lm_d.p, ctx->x.p);
   NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
   ctx->has_network = true;
   return NXFX_OK;

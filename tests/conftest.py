@@ -10,6 +10,7 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: CPU test that takes tens of seconds (still part of the default run)")
 
 
 @pytest.fixture(scope="session")

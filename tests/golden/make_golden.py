@@ -79,5 +79,17 @@ def main():
     print(f"wrote {len(data)} arrays to {HERE / 'reference_graphs.npz'}")
 
 
+def main_large():
+    """``--large``: networkx's own ``smallest_last`` colouring (mesh.py:38-39) of the 16- and the
+    20-generation ``make_tree`` (the headline graph; 84 s and ~3 GB), one int8 per edge in edge order ->
+    reference_colors_large.npz.  Pins the networkx-identical colouring NetworkMesh uses at scale."""
+    ref = load_reference_generators()
+    out = {}
+    for n in (16, 20):
+        G = ref.make_tree(n, n, n)
+        out[f"color_tree_n{n}_smallest_last"] = reference_coloring(G, "smallest_last").astype(np.int8)
+    np.savez_compressed(HERE / "reference_colors_large.npz", **out)
+
+
 if __name__ == "__main__":
-    main()
+    main_large() if "--large" in sys.argv else main()

@@ -87,6 +87,82 @@ def test_reversed_edge_keys_do_not_raise():
     assert nm.num_edge_colors == 2
 
 
+def _networkx_colors(G, strategy):
+    """mesh.py:38-39 verbatim, per edge in graph.edges() order."""
+    col = nx.coloring.greedy_color(nx.line_graph(G.to_undirected()), strategy=strategy)
+    return np.asarray([col[(u, v)] if (u, v) in col else col[(v, u)] for u, v in G.edges()], dtype=np.int32)
+
+
+@pytest.mark.parametrize("strategy", ["smallest_last", "largest_first"])
+def test_networkx_identical_coloring_equals_networkx(strategy):
+    """The set-order emulation reproduces networkx edge by edge: binary trees, arterial trees, random
+    trees with random orientation, graphs with cycles, a star and a chain."""
+    from networks_fenicsx_b200.mesh import _networkx_identical_edge_coloring
+
+    graphs = [ng.make_tree(n, 1, 1) for n in (2, 3, 6, 9, 12)]
+    graphs += [ng.make_arterial_tree(N=N, direction=np.array([0.1, 1.0, 0.0])) for N in (3, 7, 10)]
+    graphs += [helpers.random_tree(n, seed) for n, seed in ((40, 0), (300, 1), (2000, 2))]
+    graphs += [helpers.edge_info_graph(), helpers.double_junction_graph(), helpers.linear_graph(50)]
+    rng = np.random.default_rng(7)
+    for _ in range(4):  # random connected graphs with chords and mixed orientation
+        n = int(rng.integers(10, 120))
+        G = nx.DiGraph()
+        G.add_nodes_from(range(n))
+        und = set()
+        for k in range(1, n):
+            p = int(rng.integers(0, k))
+            und.add((p, k))
+            G.add_edge(*((p, k) if rng.random() < 0.5 else (k, p)))
+        for _ in range(n // 3):
+            a, b = (int(v) for v in rng.integers(0, n, 2))
+            if a != b and (min(a, b), max(a, b)) not in und:
+                und.add((min(a, b), max(a, b)))
+                G.add_edge(a, b)
+        graphs.append(G)
+    for G in graphs:
+        edges = np.asarray(list(G.edges()), dtype=np.int64)
+        mine = _networkx_identical_edge_coloring(G.number_of_nodes(), edges, strategy)
+        assert np.array_equal(mine, _networkx_colors(G, strategy)), (G.number_of_nodes(), strategy)
+
+
+def test_large_tree_coloring_is_the_reference_coloring():
+    """Above NETWORKX_COLORING_MAX_EDGES (every headline run) NetworkMesh still gives networkx's
+    ``smallest_last`` colouring: compared with fixtures that networkx itself produced for the 16- and the
+    20-generation tree (tests/golden/make_golden.py --large; 84 s / 3 GB for n = 20)."""
+    large = np.load(pathlib.Path(__file__).parent / "golden" / "reference_colors_large.npz")
+    A = ng.make_tree(16, 16, 16, as_arrays=True)
+    assert A.number_of_edges() > 60000
+    import networks_fenicsx_b200.mesh as mesh_mod
+
+    old = mesh_mod.NETWORKX_COLORING_MAX_EDGES
+    mesh_mod.NETWORKX_COLORING_MAX_EDGES = 1000  # force the large-graph path at a size the suite affords
+    try:
+        nm = nxfx.NetworkMesh(A, N=1, color_strategy="smallest_last")
+    finally:
+        mesh_mod.NETWORKX_COLORING_MAX_EDGES = old
+    assert np.array_equal(nm.edge_colors, large["color_tree_n16_smallest_last"])
+
+
+@pytest.mark.slow
+def test_headline_tree_coloring_is_the_reference_coloring():
+    """The 20-generation headline graph (1,048,575 edges): 26 s."""
+    large = np.load(pathlib.Path(__file__).parent / "golden" / "reference_colors_large.npz")
+    A = ng.make_tree(20, 20, 20, as_arrays=True)
+    nm = nxfx.NetworkMesh(A, N=1, color_strategy="smallest_last")
+    assert np.array_equal(nm.edge_colors, large["color_tree_n20_smallest_last"])
+
+
+def test_unreproducible_strategy_at_scale_warns():
+    from networks_fenicsx_b200.mesh import _large_graph_colors
+
+    A = ng.make_tree(9, 1, 1, as_arrays=True)
+    with pytest.warns(UserWarning, match="native greedy"):
+        col = _large_graph_colors(A.number_of_nodes(), A.edges, "saturation_largest_first")
+    assert col.max() == 2
+    with pytest.warns(UserWarning, match="native greedy"):
+        _large_graph_colors(A.number_of_nodes(), A.edges, lambda G, colors: list(G))
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_native_greedy_coloring_is_proper(seed):
     G = helpers.random_tree(300, seed)
