@@ -120,6 +120,86 @@ def _endpoint(pm1, p0, normal, angle_deg, length):
     return p0 + length * newdir / np.linalg.norm(newdir, axis=-1)
 
 
+def _arterial_generations_loop(N, pos, radius, edges, lmbda, gamma, normal, random):
+    """Vessel by vessel, as the reference does (any ``normal`` callable, random branching sides)."""
+    inode = 1
+    previous = [0]  # edge indices of the previous generation
+    for _ in range(1, N):
+        current = []
+        for e in previous:
+            a, b = edges[e]
+            Dp = radius[e] * 2
+            D2 = Dp * (gamma**3 + 1) ** (-1 / 3)
+            D1 = gamma * D2
+            cos1 = (Dp**4 + D1**4 - (Dp**3 - D1**3) ** (4 / 3)) / (2 * Dp**2 * D1**2)
+            cos2 = (Dp**4 + D2**4 - (Dp**3 - D2**3) ** (4 / 3)) / (2 * Dp**2 * D2**2)
+            ang1, ang2 = np.degrees(np.arccos(cos1)), np.degrees(np.arccos(cos2))
+            sign1 = 1 if not random else np.random.choice([-1, 1])
+            nrm = normal(pos[b])
+            for sign, ang, D in ((sign1, ang1, D1), (-sign1, ang2, D2)):
+                inode += 1
+                edges[inode - 1] = (b, inode)
+                pos[inode] = _endpoint(pos[a], pos[b], nrm, sign * ang, lmbda * D)
+                radius[inode - 1] = D / 2
+                current.append(inode - 1)
+        previous = current
+
+
+def _scalar_power(x: np.ndarray, p: float) -> np.ndarray:
+    """``x ** p`` element by element with the SCALAR power (what the reference's per-vessel code runs);
+    a generation holds few distinct diameters, so the scalar work is done once per distinct value."""
+    uniq, inv = np.unique(x, return_inverse=True)
+    return np.array([v**p for v in uniq], dtype=np.float64)[inv]
+
+
+def _arterial_generations_vectorised(N, pos, radius, edges, lmbda, gamma):
+    """All vessels of a generation at once (default surface normal e_z, deterministic sides).  Generation
+    g >= 2 holds the edges 2**(g-1)-1 .. 2**g-2; the daughters of the i-th edge of generation g-1 are the
+    nodes 2**(g-1)+2i and 2**(g-1)+2i+1 (creation order of the reference's loop).
+
+    Everything elementwise is done on whole generations with the reference's operations in the
+    reference's order (with the normal (0, 0, 1) the projection and ``K = [[0,-1,0],[1,0,0],[0,0,0]]``
+    are exact).  The one BLAS call of ``_endpoint`` -- the 3x3 matrix-vector product ``np.dot(rot, in_plane)``,
+    whose rounding depends on the BLAS kernel (FMA or not) -- is still issued per vessel, so the positions
+    are bit-identical to the loop form on any machine (tests/test_host_logic.py; 1 M vessels in ~3 s
+    instead of 35 s)."""
+    for g in range(2, N + 1):
+        cnt = 2 ** (g - 2)
+        par = np.arange(cnt) + (cnt - 1)
+        a, b = edges[par, 0], edges[par, 1]
+        Dp = radius[par] * 2
+        D2 = Dp * (gamma**3 + 1) ** (-1 / 3)
+        D1 = gamma * D2
+        P = _scalar_power  # numpy rounds ``array ** p`` (SIMD pow) and ``scalar ** p`` (libm pow) differently
+        cos1 = (P(Dp, 4) + P(D1, 4) - P(P(Dp, 3) - P(D1, 3), 4 / 3)) / (2 * P(Dp, 2) * P(D1, 2))
+        cos2 = (P(Dp, 4) + P(D2, 4) - P(P(Dp, 3) - P(D2, 3), 4 / 3)) / (2 * P(Dp, 2) * P(D2, 2))
+        ang1, ang2 = np.degrees(np.arccos(cos1)), np.degrees(np.arccos(cos2))
+        prev = pos[b] - pos[a]
+        in_plane = prev.copy()
+        in_plane[:, 2] = prev[:, 2] - prev[:, 2]  # x - (x . n) n with n = (0, 0, 1)
+        node0 = 2 ** (g - 1) + 2 * np.arange(cnt)
+        for k, (sgn, ang, D) in enumerate(((1.0, ang1, D1), (-1.0, ang2, D2))):
+            theta = np.radians(sgn * ang)
+            s_, c_ = np.sin(theta), 1 - np.cos(theta)
+            rot = np.zeros((cnt, 3, 3))  # I + s K + c K^2, K^2 = diag(-1, -1, 0)
+            rot[:, 0, 0] = 1.0 + c_ * -1.0
+            rot[:, 1, 1] = 1.0 + c_ * -1.0
+            rot[:, 2, 2] = 1.0
+            rot[:, 0, 1] = s_ * -1.0
+            rot[:, 1, 0] = s_
+            newdir = np.empty((cnt, 3))
+            dot = np.dot
+            for i in range(cnt):
+                newdir[i] = dot(rot[i], in_plane[i])
+            nn = np.sqrt(newdir[:, 0] * newdir[:, 0] + newdir[:, 1] * newdir[:, 1] + newdir[:, 2] * newdir[:, 2])
+            length = lmbda * D
+            node = node0 + k
+            pos[node] = pos[b] + length[:, None] * newdir / nn[:, None]
+            edges[node - 1, 0] = b
+            edges[node - 1, 1] = node
+            radius[node - 1] = D / 2
+
+
 @timed("nxfx:make_arterial_tree")
 def make_arterial_tree(
     N: int,
@@ -145,27 +225,10 @@ def make_arterial_tree(
     pos[1] = p0 + (D0 * lmbda) * direction / np.linalg.norm(direction, axis=-1)
     edges[0] = (0, 1)
     radius[0] = D0 / 2
-    inode = 1
-    previous = [0]  # edge indices of the previous generation
-    for _ in range(1, N):
-        current = []
-        for e in previous:
-            a, b = edges[e]
-            Dp = radius[e] * 2
-            D2 = Dp * (gamma**3 + 1) ** (-1 / 3)
-            D1 = gamma * D2
-            cos1 = (Dp**4 + D1**4 - (Dp**3 - D1**3) ** (4 / 3)) / (2 * Dp**2 * D1**2)
-            cos2 = (Dp**4 + D2**4 - (Dp**3 - D2**3) ** (4 / 3)) / (2 * Dp**2 * D2**2)
-            ang1, ang2 = np.degrees(np.arccos(cos1)), np.degrees(np.arccos(cos2))
-            sign1 = 1 if not random else np.random.choice([-1, 1])
-            nrm = normal(pos[b])
-            for sign, ang, D in ((sign1, ang1, D1), (-sign1, ang2, D2)):
-                inode += 1
-                edges[inode - 1] = (b, inode)
-                pos[inode] = _endpoint(pos[a], pos[b], nrm, sign * ang, lmbda * D)
-                radius[inode - 1] = D / 2
-                current.append(inode - 1)
-        previous = current
+    if normal is _default_normal and not random:
+        _arterial_generations_vectorised(N, pos, radius, edges, lmbda, gamma)
+    else:
+        _arterial_generations_loop(N, pos, radius, edges, lmbda, gamma, normal, random)
     if as_arrays:
         return ArrayGraph(pos, edges, {"radius": radius})
     import networkx as nx

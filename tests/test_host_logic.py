@@ -58,6 +58,23 @@ def test_make_arterial_tree_matches_reference_fixtures():
         ng.make_arterial_tree(3, gamma=1.5)
 
 
+def test_vectorised_arterial_tree_equals_the_per_vessel_loop():
+    """Generation-wise construction vs the reference-shaped per-vessel loop at a size the fixtures do not
+    reach (4095 vessels; the vectorised form has to use the scalar power and the per-vessel BLAS product to
+    stay bit-identical)."""
+    for N, gamma, direction in ((12, 0.8, [0.1, 1.0, 0.0]), (11, 0.5, [1.0, 1.0, 0.0])):
+        A = ng.make_arterial_tree(N=N, direction=np.array(direction), gamma=gamma, as_arrays=True)
+        pos = np.empty((2**N, 3))
+        rad = np.empty(2**N - 1)
+        ed = np.empty((2**N - 1, 2), dtype=np.int64)
+        pos[:2], ed[0], rad[0] = A.pos[:2], (0, 1), A.edge_attrs["radius"][0]
+        ng._arterial_generations_loop(N, pos, rad, ed, 8.0, gamma, ng._default_normal, False)
+        assert np.array_equal(pos, A.pos) and np.array_equal(ed, A.edges) and np.array_equal(rad, A.edge_attrs["radius"])
+    # a custom surface normal takes the loop form
+    B = ng.make_arterial_tree(N=4, normal=lambda x: np.array([0.0, 0.2, 1.0]), as_arrays=True)
+    assert B.pos.shape == (16, 3) and np.abs(B.pos[:, 2]).max() > 0
+
+
 def test_large_tree_generation_is_fast():
     A = ng.make_tree(18, 18, 18, as_arrays=True)
     assert A.number_of_edges() == 2**18 - 1 and A.pos.shape == (2**18, 3)

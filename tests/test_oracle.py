@@ -191,3 +191,32 @@ def test_symmetrised_system():
     S = S.tocsr()
     assert abs(S - S.T).max() < 1e-15
     assert abs(A - A.T).max() == 2.0
+
+
+# ---- second derivation of the element tensors: FFCx-style quadrature from the coordinate dofs ---------
+@pytest.mark.parametrize("fd,pd", [(1, 0), (2, 1), (2, 0), (3, 2), (4, 3)])
+def test_closed_form_element_tensors_equal_the_quadrature_literal(fd, pd):
+    """R h M_ref / B_ref / f h w_ref (what reference_port.py, elements.py and the CUDA kernels use) against
+    Gauss quadrature with detJ = ||J||, K = J^T/||J||^2 on randomly placed cells in 3-D; B does not depend
+    on the cell; the orientation flips B only."""
+    from networks_fenicsx_b200 import elements
+    from oracle import ffcx_literal
+
+    rng = np.random.default_rng(10 * fd + pd)
+    M_ref, B_ref, w_ref, _, _ = rp.lagrange_tables(fd, pd)
+    M_prod, B_prod, w_prod, _, _ = elements.tables(fd, pd)
+    for _ in range(5):
+        x0, x1 = rng.normal(size=3), rng.normal(size=3)
+        R, f = float(rng.uniform(0.1, 5.0)), float(rng.normal())
+        h = np.linalg.norm(x1 - x0)
+        M, B, L = ffcx_literal.cell_tensors(x0, x1, fd, pd, R=R, f=f)
+        for Mt, Bt, wt in ((M_ref, B_ref, w_ref), (M_prod, B_prod, w_prod)):
+            np.testing.assert_allclose(M, R * h * Mt, rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(B, Bt, rtol=1e-12, atol=1e-13)
+            np.testing.assert_allclose(L, f * h * wt, rtol=1e-12, atol=1e-14)
+        Mf, Bf, _ = ffcx_literal.cell_tensors(x0, x1, fd, pd, R=R, f=f, orientation=-1.0)
+        np.testing.assert_allclose(Bf, -B, rtol=0, atol=1e-15)
+        np.testing.assert_allclose(Mf, M, rtol=0, atol=0)
+    if (fd, pd) == (1, 0):
+        np.testing.assert_allclose(M_ref, [[1 / 3, 1 / 6], [1 / 6, 1 / 3]], rtol=1e-15)
+        np.testing.assert_allclose(B_ref, [[-1.0, 1.0]], rtol=1e-15)
