@@ -203,6 +203,14 @@ class HydraulicNetworkAssembler:
             return (None, float(getattr(val, "value", val)))
         arr = np.asarray(val, dtype=np.float64)
         nm = self._network_mesh
+        part = getattr(nm, "_partition", None)
+        if part is not None and arr.ndim == 1 and arr.size != nc:
+            # partitioned network: coefficients given for the GLOBAL network are restricted to this rank's edges
+            Eg, Nc = nm._global_graph.number_of_edges(), nm.cells_per_edge
+            if arr.size == Eg:
+                arr = arr[part.global_edges]
+            elif arr.size == Eg * Nc:
+                arr = arr.reshape(Eg, Nc)[part.global_edges].ravel()
         if arr.shape == (nm.graph_edges.shape[0],) and nm.cells_per_edge != 1:
             arr = np.repeat(arr, nm.cells_per_edge)
         if arr.shape != (nc,):

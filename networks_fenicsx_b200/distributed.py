@@ -132,27 +132,46 @@ class DistributedSolver:
     def __init__(self, graph: ArrayGraph, N: int, p_bc_ex, f=None, R=None, device: int = 0,
                  color_strategy="smallest_last", chunk_nodes: int = CHUNK_NODES, group=None,
                  exchange: str = "auto"):
+        import torch.distributed as dist
+
+        from .assembly import HydraulicNetworkAssembler
+        from .mesh import NetworkMesh, SerialComm
+        from .solver import Solver
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        self.part = part = partition_tree(graph, world, rank, chunk_nodes)
+        # the sub-network is handed over explicitly (comm = serial): no second partitioning inside
+        mesh = NetworkMesh(part.graph, N=N, color_strategy=color_strategy, device=device,
+                           node_degree=part.node_degree, comm=SerialComm())
+        assembler = HydraulicNetworkAssembler(mesh)
+        assembler.compute_forms(p_bc_ex=p_bc_ex, f=self._restrict(f, N, graph), R=self._restrict(R, N, graph))
+        solver = Solver(assembler, schedule=part.schedule)
+        self._attach(part, mesh, assembler, solver, group, exchange)
+
+    @classmethod
+    def from_solver(cls, solver, part: TreePartition, group=None, exchange: str = "auto") -> "DistributedSolver":
+        """Distributed layer for an existing ``Solver`` on one rank's part of a partitioned network
+        (``NetworkMesh(G, N, comm=TorchDistComm())`` under torchrun: the reference-API path)."""
+        self = cls.__new__(cls)
+        self._attach(part, solver.assembler.network, solver.assembler, solver, group, exchange)
+        return self
+
+    def _attach(self, part: TreePartition, mesh, assembler, solver, group, exchange: str) -> None:
         import ctypes as C
 
         import torch
         import torch.distributed as dist
 
         from . import _lib
-        from .assembly import HydraulicNetworkAssembler
-        from .mesh import NetworkMesh
-        from .solver import Solver
 
         self._C, self._torch, self._dist, self._group = C, torch, dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.part = partition_tree(graph, self.world, self.rank, chunk_nodes)
-        part = self.part
-        self.mesh = NetworkMesh(part.graph, N=N, color_strategy=color_strategy, device=device,
-                                node_degree=part.node_degree)
+        self.part = part
+        self.mesh, self.assembler, self.solver = mesh, assembler, solver
+        N = mesh.cells_per_edge
+        device = mesh.device.index
         assert np.array_equal(part.global_nodes[self.mesh.bifurcation_values], part.global_nodes[
             np.flatnonzero(part.node_degree > 1)])
-        self.assembler = HydraulicNetworkAssembler(self.mesh)
-        self.assembler.compute_forms(p_bc_ex=p_bc_ex, f=self._restrict(f, N, graph), R=self._restrict(R, N, graph))
-        self.solver = Solver(self.assembler, schedule=part.schedule)
         self.dev = self.mesh.device
         shared = np.ascontiguousarray(part.shared_lm, dtype=np.int32)
         weight = np.ascontiguousarray(part.lam_weight, dtype=np.float64)

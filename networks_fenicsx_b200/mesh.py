@@ -60,6 +60,33 @@ class SerialComm:
 COMM_WORLD = SerialComm()
 
 
+def _resolve_comm(comm):
+    """The reference defaults to ``MPI.COMM_WORLD`` (mesh.py:89), so the same script runs serially or
+    under ``mpiexec -n k``.  Here the launcher is ``torchrun``: with ``comm=None`` and ``WORLD_SIZE > 1`` in
+    the environment the process group is initialised (NCCL, one GPU per local rank) and a
+    ``TorchDistComm`` is returned; otherwise the serial stand-in."""
+    import os
+
+    if comm is not None:
+        return comm
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return COMM_WORLD
+    import torch
+    import torch.distributed as dist
+
+    from .parallel import TorchDistComm
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group("gloo")
+    return TorchDistComm(device=torch.device("cuda", local_rank) if torch.cuda.is_available() else None)
+
+
 # --------------------------------------------------------------------------------------------
 # colouring (mesh.py:29-42)
 # --------------------------------------------------------------------------------------------
@@ -474,20 +501,62 @@ class NetworkMesh:
         graph,
         N: int,
         color_strategy: str | Callable | Iterable | None = None,
-        comm=COMM_WORLD,
+        comm=None,
         graph_rank: int = 0,
         device: int | Device | None = None,
         node_degree: npt.NDArray[np.integer] | None = None,
     ):
         self._node_degree_override = node_degree
-        self._comm = comm if comm is not None else COMM_WORLD
+        self._comm = comm = _resolve_comm(comm)
         self._device_arg = device
+        self._partition = None  # this rank's part when the network is cut over several processes
+        self._global_graph = None
+        if getattr(comm, "size", 1) > 1 and node_degree is None:
+            graph, node_degree = self._partition_over(comm, graph, N)
+            self._node_degree_override = node_degree
+            if device is None:
+                import os
+
+                self._device_arg = int(os.environ.get("LOCAL_RANK", "0"))
         self._dev: Device | None = None
         self._x_host = None
         self._cells_host = None
         self._build_mesh(graph, N=N, color_strategy=color_strategy, comm=comm, graph_rank=graph_rank)
         self._build_network_submeshes()
         self._create_lm_submesh()
+
+    def _partition_over(self, comm, graph, N):
+        """Several processes (torchrun; the reference: ``mpiexec``, mesh.py:227-250 distributes the mesh):
+        every rank holds the whole graph (the reference builds it on ``graph_rank`` and lets DOLFINx
+        distribute the cells) and keeps its edge partition of it -- subtrees of the elimination schedule,
+        cut multipliers replicated (``distributed.partition_tree``).  Networks too small to cut, or with
+        cycles, are REPLICATED: every rank then solves the whole network redundantly, with identical
+        results.  Returns the graph this rank meshes and the global degrees of its nodes."""
+        import warnings
+
+        from .distributed import partition_tree
+
+        if isinstance(graph, ArrayGraph):
+            glob = graph
+        else:
+            nodes = np.fromiter(graph.nodes(), dtype=np.int64, count=graph.number_of_nodes())
+            if not np.array_equal(nodes, np.arange(nodes.size)):
+                raise ValueError("graph nodes must be the integers 0..n-1 in insertion order (mesh.py:183-184,274)")
+            attrs = {}
+            edges = _edge_array(graph)
+            if edges.shape[0] and all("radius" in graph.edges[e] for e in graph.edges()):
+                attrs["radius"] = np.asarray([graph.edges[e]["radius"] for e in graph.edges()], dtype=np.float64)
+            glob = ArrayGraph(np.asarray([graph.nodes[v]["pos"] for v in graph.nodes()], dtype=np.float64), edges, attrs)
+        self._global_graph = glob
+        try:
+            part = partition_tree(glob, comm.size, comm.rank)
+        except (ValueError, NotImplementedError) as exc:
+            if comm.rank == 0:
+                warnings.warn(f"the network is not cut over the {comm.size} processes ({exc}): every rank solves all of it",
+                              stacklevel=3)
+            return graph, None
+        self._partition = part
+        return part.graph, part.node_degree
 
     # ---- host-side graph analysis ---------------------------------------------------------
     @timed("nxfx:NetworkMesh:build_mesh")

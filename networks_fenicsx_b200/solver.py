@@ -48,9 +48,16 @@ class Solver:
         nm = assembler.network
         self._ksp = KSP(nm.comm)
         # symbolic phase (solver.py:43-49)
+        if kind is not None and not isinstance(kind, str):
+            # a list of lists of PETSc matrix types (solver.py:37, fem.petsc.create_matrix): a MatNest whose
+            # blocks have the given types.  Storage here is one CSR with block views either way.
+            rows = [list(r) for r in kind]
+            nb = len(assembler.block_sizes)
+            if len(rows) != nb or any(len(r) != nb for r in rows):
+                raise ValueError(f"kind as a list of lists must be {nb} x {nb} (blocks [flux colours, pressure, lm])")
+            kind = "nest"
         self._A = assembler.create_matrix(kind=kind)
         kind = "nest" if self._A.getType() == "nest" else kind
-        assert isinstance(kind, str) or kind is None
         self._b = assembler.create_vector(kind=kind)
         self._x = assembler.create_vector(kind=kind)
         self.ksp.setOperators(self.A)
@@ -68,6 +75,8 @@ class Solver:
         self.ksp.options = dict(petsc_options)
         # elimination schedule of the bifurcation graph (the analysis phase of the direct solver)
         # (``schedule``: a precomputed one, e.g. the local part of a partitioned network)
+        if schedule is None and getattr(nm, "_partition", None) is not None:
+            schedule = nm._partition.schedule  # this rank's chunks + the replicated top chunk
         self._schedule = schedule if schedule is not None else build_tree_schedule(
             nm.graph_edges, nm.node_multiplier_index, nm.bifurcation_values.size,
             root_hint_nodes=nm._boundary_out_nodes,
@@ -81,6 +90,14 @@ class Solver:
         )
         self.info = _lib.SolveInfo()
         self._x_stage = None
+        # partitioned network (NetworkMesh under torchrun): the solve goes through the distributed layer
+        self._dist = None
+        if getattr(nm, "_partition", None) is not None and not getattr(self, "_no_dist", False):
+            if assembler.is_generic:
+                raise NotImplementedError("a network cut over several GPUs needs flux degree 1 / pressure degree 0")
+            from .distributed import DistributedSolver  # noqa: PLC0415
+
+            self._dist = DistributedSolver.from_solver(self, nm._partition)
 
     @property
     def assembler(self) -> assembly.HydraulicNetworkAssembler:
@@ -137,13 +154,22 @@ class Solver:
         if self.assembler.is_generic and pc_type in _DIRECT_PCS:
             # higher-order elements: the network Schur condensation is implemented for P1/DG0;
             # direct-solver accuracy is obtained with (long-restart) GMRES instead
+            if not getattr(self, "_warned_generic_direct", False):
+                import warnings  # noqa: PLC0415
+
+                warnings.warn(
+                    f"pc_type={pc_type!r} (a direct solve) with flux/pressure degrees {self.assembler.degrees}: the exact "
+                    "network condensation exists for degrees (1, 0); this system is solved with restarted GMRES + "
+                    "flux-Jacobi to ksp_rtol (default 1e-12) and raises if that is not reached", stacklevel=3)
+                self._warned_generic_direct = True
             opts.pc_type = _lib.PC_JACOBI_FLUX
             opts.ksp_type = _lib.KSP_FGMRES
             opts.rtol = float(o.get("ksp_rtol", 1e-12))
             opts.atol = float(o.get("ksp_atol", 1e-50))
             opts.max_it = int(o.get("ksp_max_it", 20000))
             opts.restart = int(o.get("ksp_gmres_restart", min(self.assembler.num_dofs, 200)))
-            opts.error_if_not_converged = int(bool(o.get("ksp_error_if_not_converged", False)))
+            # a direct solver never hands back an unconverged iterate silently
+            opts.error_if_not_converged = int(bool(o.get("ksp_error_if_not_converged", True)))
             return opts
         if pc_type in _DIRECT_PCS:
             opts.pc_type = _lib.PC_NETWORK_SCHUR
@@ -202,13 +228,24 @@ class Solver:
         self.info = _lib.SolveInfo()
         self._A._materialise_zero()
         self._A.bind()
-        try:
-            dev.call(
-                "nxfx_solve", self._b.device_ptr(), self._x.device_ptr_overwrite(),
-                C.byref(opts), C.byref(self.info),
-            )
-        finally:
-            self._record_info()
+        if self._dist is not None:
+            hist = self._dist.solve(refine_steps=int(opts.refine_steps), final_residual=bool(opts.final_residual),
+                                    refine_rtol=float(opts.refine_rtol))
+            self.ksp.its = 1 + self._dist.corrections
+            self.ksp.history = [h * self._dist.rhs_norm for h in hist]
+            self.ksp.rnorm = self.ksp.history[-1] if hist else float("nan")
+            converged = bool(hist) and hist[-1] <= max(opts.rtol, 0.0) or not hist
+            self.ksp.reason = 2 if converged else -3
+            if not converged and opts.error_if_not_converged:
+                raise RuntimeError(f"nxfx_solve failed (-3): linear solve did not converge: relative residual {hist[-1]:.3e}")
+        else:
+            try:
+                dev.call(
+                    "nxfx_solve", self._b.device_ptr(), self._x.device_ptr_overwrite(),
+                    C.byref(opts), C.byref(self.info),
+                )
+            finally:
+                self._record_info()
         self._x.mark_device_modified()
         # fem.petsc.assign: split the blocked vector into the functions (solver.py:134)
         if sum(fn.x.array.size for fn in functions) != self._x.n:

@@ -88,3 +88,43 @@ def test_partition_rejects_cycles_and_tiny_graphs():
         partition_tree(G, 2, 0)
     with pytest.raises(ValueError):
         partition_tree(ng.make_tree(2, 1, 1, as_arrays=True), 4, 0)
+
+
+def test_network_mesh_partitions_transparently_under_a_multi_rank_comm():
+    """NetworkMesh(G, N, comm=<size 2>) keeps this rank's part (reference: mesh.py:84-96 under mpiexec);
+    too-small / cyclic networks are replicated with a warning."""
+    import types
+
+    import networkx as nx
+    import pytest
+
+    import networks_fenicsx_b200 as nxfx
+    from networks_fenicsx_b200.distributed import partition_tree
+
+    G = ng.make_tree(9, 9, 9, as_arrays=True)
+    sizes = []
+    for rank in range(2):
+        comm = types.SimpleNamespace(size=2, rank=rank)
+        nm = nxfx.NetworkMesh(G, N=2, color_strategy="smallest_last", comm=comm, device=0)
+        part = partition_tree(G, 2, rank)
+        assert nm._partition is not None and np.array_equal(nm._partition.global_edges, part.global_edges)
+        assert np.array_equal(nm.graph_edges, part.graph.edges)
+        assert np.array_equal(nm.bifurcation_values, np.flatnonzero(part.node_degree > 1))
+        sizes.append(nm.graph_edges.shape[0])
+    assert sum(sizes) == G.number_of_edges()
+    # a networkx graph with edge attributes is cut the same way
+    Gx = ng.make_arterial_tree(N=8, direction=np.array([0.1, 1.0, 0.0]))
+    nm = nxfx.NetworkMesh(Gx, N=1, comm=types.SimpleNamespace(size=2, rank=1), device=0)
+    assert nm._partition is not None and "radius" in nm._global_graph.edge_attrs
+    # too small to cut -> replicated, with a warning on rank 0
+    with pytest.warns(UserWarning, match="every rank solves all of it"):
+        nm = nxfx.NetworkMesh(ng.make_tree(2, 1, 3), N=4, comm=types.SimpleNamespace(size=2, rank=0), device=0)
+    assert nm._partition is None and nm.graph_edges.shape[0] == 3
+    Gc = nx.DiGraph()
+    for i, p in enumerate([(0, 0), (0, 1), (1, 2), (-1, 2), (0, 3), (0, 4)]):
+        Gc.add_node(i, pos=np.array(p, dtype=float))
+    for e in [(0, 1), (1, 2), (1, 3), (2, 4), (3, 4), (4, 5)]:
+        Gc.add_edge(*e)
+    with pytest.warns(UserWarning):
+        nm = nxfx.NetworkMesh(Gc, N=2, comm=types.SimpleNamespace(size=2, rank=0), device=0)
+    assert nm._partition is None
