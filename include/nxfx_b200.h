@@ -224,19 +224,24 @@ int nxfx_assemble_generic(nxfx_ctx* ctx, const double* R_cell_d, double R_const,
 /* ---- (6) multi-GPU: one rank's part of a partitioned network ------------------------------------ *
  * Replaces what MPI does inside DOLFINx/PETSc/MUMPS at assembly.py:355-367 and solver.py:127-132
  * (stash exchange, ghost updates, distributed LU).  The ctx holds one rank's sub-network in which
- * the multipliers of the cut bifurcations are REPLICATED (see networks_fenicsx_b200/distributed.py).
- * Every quantity that couples ranks is additive; the caller all-reduces (SUM) the small buffers
- * between the begin/end halves with its own communicator (torch.distributed / NCCL):
- *   shared_lm_h [n_shared]   local multiplier indices of the replicated multipliers
+ * the multipliers of the SHARED bifurcations -- the nodes of the elimination tree whose subtree spans
+ * several ranks: world-1 of them for a balanced binary tree -- are REPLICATED (see
+ * networks_fenicsx_b200/distributed.py); the rest of the top of the tree is private to one rank.
+ * Every quantity that couples ranks is additive.  Either the library exchanges it itself (nxfx_comm_*
+ * below: in-kernel, over NVLink), or the caller all-reduces (SUM) the small buffers between the
+ * begin/end halves with its own communicator (torch.distributed / NCCL):
+ *   shared_lm_h [n_shared]   local multiplier indices of the shared multipliers, in an order that is
+ *                            the same on every rank (ascending global node id); they must belong to
+ *                            the LAST chunk of the schedule
  *   lam_weight_h [n_bif]     1 where this rank counts the multiplier row (norms, -r_lambda), else 0
- *   buf_d                    caller-owned device buffer, 2*n_top doubles (nxfx_top_size)
- *   nxfx_pc_setup_begin  -> buf = [partial pivots | link conductances] of the top chunk
- *   nxfx_pc_setup_end    <- all-reduced buf: factorises the top chunk (identically on all ranks)
- *   nxfx_pc_apply_begin  -> buf[0:n_top] = partial right-hand side of the top chunk (may be called
+ *   buf_d                    caller-owned device buffer, n_shared-sized sections (nxfx_top_size)
+ *   nxfx_pc_setup_begin  -> buf = [partial pivots | link conductances] of the shared nodes (2 n_shared)
+ *   nxfx_pc_setup_end    <- all-reduced buf: factorises the top chunk
+ *   nxfx_pc_apply_begin  -> buf[0:n_shared] = partial right-hand side of the shared nodes (may be called
  *                        right after nxfx_pc_setup_begin with a second buffer: setup and first
  *                        application then share ONE all-reduce, followed by _setup_end, _apply_end)
  *   nxfx_pc_apply_end    <- all-reduced buf: top solve, back-substitution; z = or += P^{-1} r
- *   nxfx_pc_setup_apply_begin / _end  the recommended form of that fused sequence: buf = 3*n_top
+ *   nxfx_pc_setup_apply_begin / _end  the recommended form of that fused sequence: buf = 3*n_shared
  *                        doubles [partial pivots | link conductances | partial right-hand side],
  *                        one all-reduce in between, z = P^{-1} r.  With one cell per edge the
  *                        bottom chunks are factorised WHILE their right-hand sides are eliminated.
@@ -266,7 +271,7 @@ int nxfx_comm_create(nxfx_ctx* ctx, int32_t rank, int32_t nranks, void* handle_o
                      int32_t* slot_doubles);
 int nxfx_comm_connect(nxfx_ctx* ctx, const void* handles_all_h);
 int nxfx_comm_destroy(nxfx_ctx* ctx);
-int nxfx_top_size(nxfx_ctx* ctx, int32_t* n_top);
+int nxfx_top_size(nxfx_ctx* ctx, int32_t* n_shared); /* size of one exchanged section */
 int nxfx_pc_setup_begin(nxfx_ctx* ctx, double* buf_d);
 int nxfx_pc_setup_end(nxfx_ctx* ctx, double* buf_d);
 int nxfx_pc_apply_begin(nxfx_ctx* ctx, const double* r_d, double* buf_d);

@@ -38,7 +38,11 @@ struct DevBuf {
 
 struct TreeSchedule {
   bool set = false;
-  int n_chunks = 0, n_lvl_ptr = 0, n_chords = 0, n_top = 0;
+  int n_chunks = 0, n_lvl_ptr = 0, n_chords = 0, n_top = 0;  // n_top: nodes of the (local) top chunk
+  int top_b0 = 0;                     // first schedule index of the top chunk
+  std::vector<int32_t> t_of_bif_h;    // host copy (positions of the shared multipliers in the top chunk)
+  std::vector<int32_t> top_lvl_h;     // level table of the top chunk (schedule indices)
+  int sh_lmax = -1, pr_lmin = 0;      // level ranges of the shared / private nodes of the top chunk
   int cap = 2048;  // chunk capacity of the shared-memory sweeps
   DevBuf<int32_t> bif_of_t, chunk_desc, t_inc_ptr;
   DevBuf<int2> t_inc;
@@ -124,6 +128,8 @@ struct nxfx_ctx {
   // multi-GPU: replicated multipliers
   int32_t n_shared = 0;
   nxfx::DevBuf<int32_t> shared_lm;
+  std::vector<int32_t> shared_lm_h;
+  nxfx::DevBuf<int32_t> top_sh_pos;  // [n_shared] position of every shared multiplier inside the top chunk
   nxfx::DevBuf<double> lam_weight, lam_nonshared;
   nxfx::PeerComm comm;
   // e2e staging

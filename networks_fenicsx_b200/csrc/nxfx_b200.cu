@@ -53,6 +53,10 @@ TreeDev make_tree(nxfx_ctx* c) {
   t.t_inc = s.t_inc.p;
   t.lam_nat = s.lam_nat.p;
   t.cap = s.cap;
+  t.top_sh_pos = c->top_sh_pos.p;
+  t.n_sh = c->top_sh_pos.p ? c->n_shared : 0;
+  t.sh_lmax = s.sh_lmax;
+  t.pr_lmin = s.pr_lmin;
   t.t_parent = s.t_parent.p;
   t.t_pedge = s.t_pedge.p;
   t.t_pslot = s.t_pslot.p;
@@ -90,6 +94,36 @@ template <typename T>
 int upload(nxfx_ctx* ctx, DevBuf<T>& buf, const T* src, size_t n) {
   NXFX_CUDA(ctx, buf.alloc(n));
   if (n) NXFX_CUDA(ctx, cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return NXFX_OK;
+}
+
+// positions of the shared multipliers inside the top chunk (needs both the schedule and the shared list)
+int update_top_shared(nxfx_ctx* ctx) {
+  ctx->top_sh_pos.release();
+  ctx->tree.sh_lmax = -1;
+  ctx->tree.pr_lmin = 0;
+  if (!ctx->tree.set || ctx->n_shared == 0 || ctx->tree.t_of_bif_h.empty()) return NXFX_OK;
+  std::vector<int32_t> pos((size_t)ctx->n_shared);
+  for (int32_t i = 0; i < ctx->n_shared; ++i) {
+    const int32_t p = ctx->tree.t_of_bif_h[ctx->shared_lm_h[i]] - ctx->tree.top_b0;
+    if (p < 0 || p >= ctx->tree.n_top)
+      return fail(ctx, NXFX_ERR_INVALID, "shared multiplier %d is not in the top chunk of the schedule", ctx->shared_lm_h[i]);
+    pos[i] = p;
+  }
+  NXFX_CUDA(ctx, ctx->top_sh_pos.alloc(pos.size()));
+  NXFX_CUDA(ctx, cudaMemcpy(ctx->top_sh_pos.p, pos.data(), pos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  // level ranges: shared nodes live in levels [0, sh_lmax], private ones in [pr_lmin, nl)
+  const std::vector<int32_t>& lv = ctx->tree.top_lvl_h;
+  const int nl = (int)lv.size() - 1;
+  std::vector<char> is_sh((size_t)ctx->tree.n_top, 0);
+  for (int32_t p : pos) is_sh[p] = 1;
+  ctx->tree.sh_lmax = -1;
+  ctx->tree.pr_lmin = nl;
+  for (int L = 0; L < nl; ++L)
+    for (int n = lv[L]; n < lv[L + 1]; ++n) {
+      if (is_sh[n - ctx->tree.top_b0]) ctx->tree.sh_lmax = L;
+      else ctx->tree.pr_lmin = std::min(ctx->tree.pr_lmin, L);
+    }
   return NXFX_OK;
 }
 
@@ -407,12 +441,13 @@ int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z, bool add = fals
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ctx->pdl_coop_refused ? 1 : 2;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, tree_factor_solve_coop_kernel, t, nb, tk, fl, ep, fin, pc);
+  auto kern = pc.nranks > 1 ? tree_factor_solve_coop_kernel<true> : tree_factor_solve_coop_kernel<false>;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, t, nb, tk, fl, ep, fin, pc);
   if (le != cudaSuccess && cfg.numAttrs == 2) {
     cudaGetLastError();
     ctx->pdl_coop_refused = true;
     cfg.numAttrs = 1;
-    le = cudaLaunchKernelEx(&cfg, tree_factor_solve_coop_kernel, t, nb, tk, fl, ep, fin, pc);
+    le = cudaLaunchKernelEx(&cfg, kern, t, nb, tk, fl, ep, fin, pc);
   }
   NXFX_CUDA(ctx, le);
   ctx->launches++;
@@ -826,6 +861,9 @@ int nxfx_set_network(nxfx_ctx* ctx, int32_t n_nodes, int32_t n_edges, int32_t gd
   ctx->edge_slot_h.assign(edge_slot, edge_slot + E);
   ctx->n_shared = 0;
   ctx->shared_lm.release();
+  ctx->shared_lm_h.clear();
+  ctx->top_sh_pos.release();
+  ctx->tree.t_of_bif_h.clear();
   ctx->lam_weight.release();
   ctx->lam_nonshared.release();
   ctx->tree.set = false;
@@ -1088,6 +1126,9 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
   if ((rc = upload(ctx, s.chord_edge, chord_edge, (size_t)std::max(0, n_chords)))) return rc;
   s.n_chunks = n_chunks; s.n_lvl_ptr = n_lvl_ptr; s.n_chords = n_chords;
   s.n_top = lvl_ptr[chunk_lptr[n_chunks]] - lvl_ptr[chunk_lptr[n_chunks - 1]];
+  s.top_b0 = lvl_ptr[chunk_lptr[n_chunks - 1]];
+  s.t_of_bif_h.assign(t_of_bif, t_of_bif + nb);
+  s.top_lvl_h.assign(lvl_ptr + chunk_lptr[n_chunks - 1], lvl_ptr + chunk_lptr[n_chunks] + 1);
   // shared-memory sweeps need every chunk (nodes, levels) to fit the on-chip tables
   s.fast_ok = true;
   int max_nodes = 0, max_links = 0;
@@ -1126,9 +1167,11 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
     NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_top_fs_kernel<kFinish>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes_fs(kChunkCapMax)));
     s.coop_fs_ok = false;
     per_sm = 0;
-    if (s.coop_ok && cudaFuncSetAttribute(tree_factor_solve_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (s.coop_ok && cudaFuncSetAttribute(tree_factor_solve_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)tree_smem_bytes_fs(kChunkCapMax)) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_factor_solve_coop_kernel, kTreeThreads,
+        cudaFuncSetAttribute(tree_factor_solve_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)tree_smem_bytes_fs(kChunkCapMax)) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_factor_solve_coop_kernel<true>, kTreeThreads,
                                                       tree_smem_bytes_fs(ctx->tree.cap)) == cudaSuccess)
       s.coop_fs_ok = n_chunks <= per_sm * ctx->sm_count;  // bottom blocks + one block for the top chunk
     cudaGetLastError();
@@ -1149,7 +1192,7 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
   NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   s.set = true;
   ctx->pc_ready = false;
-  return NXFX_OK;
+  return update_top_shared(ctx);
 }
 
 int nxfx_pc_setup(nxfx_ctx* ctx) {
@@ -1334,7 +1377,8 @@ int nxfx_set_shared(nxfx_ctx* ctx, int32_t n_shared, const int32_t* shared_lm, c
   if ((rc = upload(ctx, ctx->lam_nonshared, nonshared.data(), (size_t)ctx->n_bif))) return rc;
   NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->n_shared = n_shared;
-  return NXFX_OK;
+  ctx->shared_lm_h.assign(shared_lm, shared_lm + n_shared);
+  return update_top_shared(ctx);
 }
 
 static int dist_ready(nxfx_ctx* ctx, const double* buf) {
@@ -1342,13 +1386,14 @@ static int dist_ready(nxfx_ctx* ctx, const double* buf) {
                "needs a tree schedule that fits the shared-memory sweeps and a buffer");
   NXFX_REQUIRE(ctx, ctx->cur && ctx->cur->acc_count <= 1,
                "the partitioned solve does not take a matrix accumulated over several assemblies");
+  NXFX_REQUIRE(ctx, ctx->n_shared == 0 || ctx->top_sh_pos.p, "nxfx_set_shared / nxfx_set_tree_schedule have not both been called");
   return NXFX_OK;
 }
 
 int nxfx_top_size(nxfx_ctx* ctx, int32_t* n_top) {
   if (!ctx || !n_top) return NXFX_ERR_INVALID;
   NXFX_REQUIRE(ctx, ctx->tree.set && ctx->tree.n_chunks >= 1, "no tree schedule");
-  *n_top = ctx->tree.n_top;
+  *n_top = ctx->n_shared;  // the exchanged part of the top chunk
   return NXFX_OK;
 }
 
@@ -1436,7 +1481,7 @@ int nxfx_pc_setup_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
   int rc = dist_ready(ctx, buf);
   if (rc) return rc;
   NXFX_REQUIRE(ctx, is_assembled(ctx), "assemble the matrix before pc_setup");
-  const int nt = std::max(ctx->tree.n_top, 1);
+  const int nt = std::max(ctx->n_shared, 1);
   if (ctx->N != 1) {
     if ((rc = nxfx_pc_setup_begin(ctx, buf))) return rc;
     return nxfx_pc_apply_begin(ctx, r, buf + 2 * (size_t)nt);
@@ -1457,7 +1502,7 @@ int nxfx_pc_setup_apply_end(nxfx_ctx* ctx, const double* r, double* z, double* b
   if (!ctx || !r || !z) return NXFX_ERR_INVALID;
   int rc = dist_ready(ctx, buf);
   if (rc) return rc;
-  const int nt = std::max(ctx->tree.n_top, 1);
+  const int nt = std::max(ctx->n_shared, 1);
   if (ctx->N != 1) {
     if ((rc = nxfx_pc_setup_end(ctx, buf))) return rc;
     return nxfx_pc_apply_end(ctx, r, z, buf + 2 * (size_t)nt, 0);
@@ -1501,12 +1546,16 @@ int nxfx_comm_create(nxfx_ctx* ctx, int32_t rank, int32_t nranks, void* handle_o
   if (!ctx || !handle_out) return NXFX_ERR_INVALID;
   NXFX_REQUIRE(ctx, nranks >= 2 && nranks <= kMaxPeers && rank >= 0 && rank < nranks, "bad rank / nranks");
   NXFX_REQUIRE(ctx, ctx->tree.set && ctx->lam_nonshared.p, "call nxfx_set_tree_schedule and nxfx_set_shared first");
+  // the exchange lives in the fused cooperative tree kernel: one cell per edge, all chunks of this rank co-resident
+  if (!(ctx->N == 1 && ctx->tree.fast_ok && ctx->tree.coop_fs_ok && ctx->tree.n_chunks > 1 && ctx->pipe_ok))
+    return fail(ctx, NXFX_ERR_UNSUPPORTED, "the in-kernel exchange needs one cell per edge and a schedule whose %d chunks fit "
+                "the cooperative tree kernel at once; use the split phases (nxfx_pc_*_begin/_end) instead", ctx->tree.n_chunks);
   static_assert(sizeof(cudaIpcMemHandle_t) == NXFX_COMM_HANDLE_BYTES, "handle size");
   nxfx_comm_destroy(ctx);
   PeerComm& c = ctx->comm;
   c.rank = rank;
   c.nranks = nranks;
-  c.slot = (std::max(3 * std::max(ctx->tree.n_top, 1), ctx->n_shared + 2) + 1) & ~1;
+  c.slot = 2 * ((3 * std::max(ctx->n_shared, 1) + 1) & ~1);  // 3 n_shared values (>= n_shared + 2), two 8-byte words each
   NXFX_CUDA(ctx, cudaMalloc(&c.local, comm_bytes(c)));
   NXFX_CUDA(ctx, cudaMemset(c.local, 0, comm_bytes(c)));
   NXFX_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&c.err_h), sizeof(int), cudaHostAllocMapped));

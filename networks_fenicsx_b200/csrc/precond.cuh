@@ -43,6 +43,11 @@ struct TreeDev {
   double* lam;      // schedule order
   double* lam_nat;  // natural (bifurcation) order, read by the back-substitution
   int cap;          // chunk capacity of the shared-memory sweeps (2048 or 4096)
+  // multi-GPU: the SHARED nodes of this rank's top chunk (positions inside the chunk, in the global order
+  // every rank uses); the other top-chunk nodes are private to the rank and complete without exchange
+  const int32_t* __restrict__ top_sh_pos;
+  int n_sh;
+  int sh_lmax, pr_lmin;  // deepest level of the top chunk holding a shared node / shallowest holding a private one
 };
 
 // N == 1 fusion: the tree kernels can evaluate a node's Laplacian diagonal / right-hand side on the
@@ -282,9 +287,20 @@ struct TreeSmem {  // view of the dynamic shared memory of a tree kernel
   int* lvl;   // [kLevelCap + 3]
   int* last;
 };
+// behind `last`: uint32 shbits[cap / 32] -- top chunk of a partitioned network: bit i = node i is SHARED
+// (replicated, exchanged), else private to this rank.  A bit array, not bytes: two resident blocks must stay
+// below the 196 KB shared-memory carve-out (2 KB more per block pushed the SM to the next carve-out, halved
+// its L1 and cost the staging gathers 10 us).  Not a member of the view: the single-GPU kernels run at the
+// 32-register limit and must not carry a pointer they never use.
+__device__ __forceinline__ unsigned int* tree_shbits(const TreeSmem& S) {
+  return reinterpret_cast<unsigned int*>(S.last + 1);
+}
+__device__ __forceinline__ bool tree_shared(const TreeSmem& S, int i) {
+  return (tree_shbits(S)[i >> 5] >> (i & 31)) & 1u;
+}
 
 __host__ __device__ constexpr size_t tree_smem_bytes(int cap) {
-  return (size_t)cap * (3 * sizeof(double) + 4 * sizeof(int)) + (size_t)(4 + kLevelCap + 3 + 1) * sizeof(int);
+  return (size_t)cap * (3 * sizeof(double) + 4 * sizeof(int)) + (size_t)(4 + kLevelCap + 3 + 1) * sizeof(int) + (size_t)cap / 8;
 }
 
 __device__ __forceinline__ TreeSmem tree_view(unsigned char* raw, int cap) {
@@ -314,6 +330,10 @@ __device__ __forceinline__ ChunkInfo load_chunk_info(const TreeDev& t, int chunk
 }
 
 // leaf -> root over the chunk's levels: block phase for the wide levels, one warp for the narrow top
+// `which` (top chunk of a partitioned network): the heavy nodes private to this rank are eliminated first
+// (kPrivateNodes), the shared ones after their partial sums have been exchanged (kSharedNodes).
+enum { kPrivateNodes = 1, kSharedNodes = 2 };
+
 template <typename NodeOp>
 __device__ __forceinline__ void sweep_up(const TreeSmem& S, const ChunkInfo& ci, NodeOp op) {
   const int tid = threadIdx.x;
@@ -327,6 +347,38 @@ __device__ __forceinline__ void sweep_up(const TreeSmem& S, const ChunkInfo& ci,
       __syncwarp();
     }
   }
+  __syncthreads();
+}
+
+// Partitioned network, top chunk: only the private (which = kPrivateNodes) or only the shared nodes, and only
+// the levels [Llo, Lhi] that hold such nodes (the private nodes sit in the deep levels of the top chunk, the
+// shared ones in the shallow levels: a level without selected nodes would still cost its barrier).
+template <typename NodeOp>
+__device__ __forceinline__ void sweep_up_sel(const TreeSmem& S, const ChunkInfo& ci, NodeOp op, int which, int Llo, int Lhi) {
+  const int tid = threadIdx.x;
+  Lhi = min(Lhi, ci.nl - 1);
+  auto take = [&](int n) { return tree_shared(S, n - ci.b0) == (which == kSharedNodes); };
+  for (int L = Lhi; L > ci.Lw && L >= Llo; --L) {
+    for (int n = S.lvl[L] + tid; n < S.lvl[L + 1]; n += blockDim.x)
+      if (take(n)) op(n);
+    __syncthreads();
+  }
+  if (tid < 32) {
+    for (int L = min(ci.Lw, Lhi); L >= Llo; --L) {
+      for (int n = S.lvl[L] + tid; n < S.lvl[L + 1]; n += 32)
+        if (take(n)) op(n);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+}
+
+// top chunk: flags of the shared nodes (all zero on a single GPU)
+__device__ __forceinline__ void load_shared_flags(const TreeDev& t, const ChunkInfo& ci, const TreeSmem& S) {
+  unsigned int* bits = tree_shbits(S);
+  for (int w = threadIdx.x; w < t.cap / 32; w += blockDim.x) bits[w] = 0u;
+  __syncthreads();
+  for (int k = threadIdx.x; k < t.n_sh; k += blockDim.x) atomicOr(bits + (t.top_sh_pos[k] >> 5), 1u << (t.top_sh_pos[k] & 31));
   __syncthreads();
 }
 
@@ -353,24 +405,58 @@ __device__ __forceinline__ void load_children(const TreeDev& t, const ChunkInfo&
   for (int i = threadIdx.x; i < ci.ce - ci.cb; i += blockDim.x) S.cidx[i] = t.t_cidx[ci.cb + i];
 }
 
-// Phases of the top chunk (multi-GPU): kPartial stops after folding in this rank's bottom-chunk
-// children and writes the partial sums to `buf` (all-reduced by the caller); kFinish starts from
-// the all-reduced buffer.  kFull = single GPU.
+// Phases of the top chunk (multi-GPU, host-driven all-reduce): kPartial stops after folding in this
+// rank's bottom-chunk children, parks the partial sums of ALL top-chunk nodes in global scratch and packs
+// those of the SHARED nodes (t.top_sh_pos) into `buf` (all-reduced by the caller); kFinish reloads the
+// scratch and takes the shared nodes from the all-reduced buffer.  kFull = single GPU.
 enum { kFull = 0, kPartial = 1, kFinish = 2 };
 
 // numeric factorisation of one chunk: d_n = diag0_n - sum_c tg_c * gd_c, gd_n = tg_n / d_n;
 // t.d receives 1/d.  `top`: children below b0 live in bottom chunks (already written to HBM).
-// buf (top chunk, kPartial/kFinish): [partial d | tg], 2*nn doubles.
+// Partitioned network (t.n_sh > 0, top chunk): kPartial eliminates the nodes PRIVATE to this rank, folds them
+// into their shared parents and packs [partial d | tg] of the shared nodes into buf (2 * n_sh doubles);
+// kFinish takes the all-reduced buf and eliminates the shared nodes (identically on every rank).
 __device__ __forceinline__ void factor_chunk(const TreeDev& t, const TreeSmem& S, int chunk, bool top,
                                              int phase = kFull, double* buf = nullptr,
                                              const FusedN1* f = nullptr) {
   const ChunkInfo ci = load_chunk_info(t, chunk, S);
   const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
+  const int ns = top ? t.n_sh : 0;
   load_children(t, ci, S);
   for (int i = tid; i < nn; i += nth) S.par[i] = t.t_parent[b0 + i];
+  if (top && phase != kFull) load_shared_flags(t, ci, S);
+  auto eliminate = [&](bool shared_children_only) {
+    return [&, shared_children_only](int n) {
+      const int i = n - b0;
+      double acc = S.a[i];
+      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+        const int c = S.cidx[k] - b0;
+        if (c >= 0 && (!shared_children_only || tree_shared(S, c))) acc -= S.b[c] * S.c[c];
+      }
+      const double inv = 1.0 / acc;
+      S.a[i] = inv;
+      S.c[i] = S.b[i] * inv;
+    };
+  };
   if (phase == kFinish) {
-    for (int i = tid; i < nn; i += nth) { S.a[i] = buf[i]; S.b[i] = buf[nn + i]; }
-  } else if (f) {
+    // private nodes: final (1/d, gd) from kPartial; shared nodes: the all-reduced partial sums
+    for (int i = tid; i < nn; i += nth) { S.a[i] = t.d[b0 + i]; S.c[i] = t.gd[b0 + i]; S.b[i] = 0.0; }
+    __syncthreads();
+    for (int k = tid; k < ns; k += nth) {
+      const int j = t.top_sh_pos[k];
+      S.a[j] = buf[k];
+      S.b[j] = buf[ns + k];
+    }
+    __syncthreads();
+    sweep_up_sel(S, ci, eliminate(true), kSharedNodes, 0, t.sh_lmax);
+    for (int k = tid; k < ns; k += nth) {
+      const int j = t.top_sh_pos[k];
+      t.d[b0 + j] = S.a[j];
+      t.gd[b0 + j] = S.c[j];
+    }
+    return;
+  }
+  if (f) {
     for (int i = tid; i < nn; i += nth) {
       S.a[i] = n1_node_diag(*f, t, b0 + i);
       const int pe = t.t_pslot[b0 + i];
@@ -384,7 +470,7 @@ __device__ __forceinline__ void factor_chunk(const TreeDev& t, const TreeSmem& S
     for (int i = tid; i < nn; i += nth) { S.a[i] = t.diag0[b0 + i]; S.b[i] = t.tg[b0 + i]; }
   }
   __syncthreads();
-  if (top && phase != kFinish) {
+  if (top) {
     for (int i = tid; i < nn; i += nth) {
       double acc = S.a[i];
       for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
@@ -395,24 +481,42 @@ __device__ __forceinline__ void factor_chunk(const TreeDev& t, const TreeSmem& S
     }
     __syncthreads();
   }
-  if (phase == kPartial) {
-    for (int i = tid; i < nn; i += nth) { buf[i] = S.a[i]; buf[nn + i] = S.b[i]; }
+  if (phase == kFull) {  // single GPU / bottom chunk: the plain sweep
+    sweep_up(S, ci, [&](int n) {
+      const int i = n - b0;
+      double acc = S.a[i];
+      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+        const int c = S.cidx[k] - b0;
+        if (c >= 0) acc -= S.b[c] * S.c[c];
+      }
+      const double inv = 1.0 / acc;
+      S.a[i] = inv;
+      S.c[i] = S.b[i] * inv;
+    });
+    for (int i = tid; i < nn; i += nth) { t.d[b0 + i] = S.a[i]; t.gd[b0 + i] = S.c[i]; }
     return;
   }
-  if (phase == kFinish)
-    for (int i = tid; i < nn; i += nth) t.tg[b0 + i] = S.b[i];  // all-reduced link conductances
-  sweep_up(S, ci, [&](int n) {
-    const int i = n - b0;
-    double acc = S.a[i];
-    for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
-      const int c = S.cidx[k] - b0;
-      if (c >= 0) acc -= S.b[c] * S.c[c];
+  // kPartial
+  sweep_up_sel(S, ci, eliminate(false), kPrivateNodes, t.pr_lmin, 1 << 30);
+  for (int k = tid; k < ns; k += nth) {  // private children of the shared nodes
+    const int j = t.top_sh_pos[k];
+    double acc = S.a[j];
+    for (int q = S.cptr[j]; q < S.cptr[j + 1]; ++q) {
+      const int c = S.cidx[q] - b0;
+      if (c >= 0 && !tree_shared(S, c)) acc -= S.b[c] * S.c[c];
     }
-    const double inv = 1.0 / acc;
-    S.a[i] = inv;
-    S.c[i] = S.b[i] * inv;
-  });
-  for (int i = tid; i < nn; i += nth) { t.d[b0 + i] = S.a[i]; t.gd[b0 + i] = S.c[i]; }
+    S.a[j] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < nn; i += nth) {
+    t.d[b0 + i] = S.a[i];                       // private: 1/d (final); shared: partial d
+    t.gd[b0 + i] = tree_shared(S, i) ? S.b[i] : S.c[i];  // private: gd (final); shared: link conductance
+  }
+  for (int k = tid; k < ns; k += nth) {
+    const int j = t.top_sh_pos[k];
+    buf[k] = S.a[j];
+    buf[ns + k] = S.b[j];
+  }
 }
 
 // stage a chunk for the solve: a = r, b = 1/d, c = gd, par
@@ -427,15 +531,37 @@ __device__ __forceinline__ void load_solve_chunk(const TreeDev& t, const ChunkIn
   }
 }
 
+// forward elimination of a staged chunk (S.a = r, S.b = 1/d, S.c = gd): r_n += sum_c gd_c r_c.
+// Partitioned network (top chunk): kPartial eliminates the private nodes, folds them into their shared
+// parents, parks everything in scratch (t.lam) and packs the partial right-hand sides of the shared nodes
+// into buf (n_sh doubles); kFinish continues from the all-reduced buf with the shared nodes.
 __device__ __forceinline__ void solve_up(const TreeDev& t, const TreeSmem& S, const ChunkInfo& ci, bool top,
                                          int phase = kFull, double* buf = nullptr) {
-  const int b0 = ci.b0, nn = ci.b1 - ci.b0;
+  const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
+  const int ns = top ? t.n_sh : 0;
+  if (top && phase != kFull) load_shared_flags(t, ci, S);
+  auto eliminate = [&](bool shared_children_only) {
+    return [&, shared_children_only](int n) {
+      const int i = n - b0;
+      double acc = S.a[i];
+      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+        const int c = S.cidx[k] - b0;
+        if (c >= 0 && (!shared_children_only || tree_shared(S, c))) acc += S.c[c] * S.a[c];
+      }
+      S.a[i] = acc;
+    };
+  };
   if (phase == kFinish) {
-    for (int i = threadIdx.x; i < nn; i += blockDim.x) S.a[i] = buf[i];
+    for (int i = tid; i < nn; i += nth) S.a[i] = t.lam[b0 + i];  // scratch of kPartial
     __syncthreads();
+    for (int k = tid; k < ns; k += nth) S.a[t.top_sh_pos[k]] = buf[k];
+    __syncthreads();
+    sweep_up_sel(S, ci, eliminate(true), kSharedNodes, 0, t.sh_lmax);
+    for (int i = tid; i < nn; i += nth) t.r[b0 + i] = S.a[i];
+    return;
   }
-  if (top && phase != kFinish) {
-    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+  if (top) {
+    for (int i = tid; i < nn; i += nth) {
       double acc = S.a[i];
       for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
         const int c = S.cidx[k];
@@ -445,19 +571,33 @@ __device__ __forceinline__ void solve_up(const TreeDev& t, const TreeSmem& S, co
     }
     __syncthreads();
   }
-  if (phase == kPartial) {
-    for (int i = threadIdx.x; i < nn; i += blockDim.x) buf[i] = S.a[i];
+  if (phase == kFull) {  // single GPU / bottom chunk: the plain sweep
+    sweep_up(S, ci, [&](int n) {
+      const int i = n - b0;
+      double acc = S.a[i];
+      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+        const int c = S.cidx[k] - b0;
+        if (c >= 0) acc += S.c[c] * S.a[c];
+      }
+      S.a[i] = acc;
+    });
+    for (int i = tid; i < nn; i += nth) t.r[b0 + i] = S.a[i];
     return;
   }
-  sweep_up(S, ci, [&](int n) {
-    const int i = n - b0;
-    double acc = S.a[i];
-    for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
-      const int c = S.cidx[k] - b0;
-      if (c >= 0) acc += S.c[c] * S.a[c];
+  // kPartial
+  sweep_up_sel(S, ci, eliminate(false), kPrivateNodes, t.pr_lmin, 1 << 30);
+  for (int k = tid; k < ns; k += nth) {
+    const int j = t.top_sh_pos[k];
+    double acc = S.a[j];
+    for (int q = S.cptr[j]; q < S.cptr[j + 1]; ++q) {
+      const int c = S.cidx[q] - b0;
+      if (c >= 0 && !tree_shared(S, c)) acc += S.c[c] * S.a[c];
     }
-    S.a[i] = acc;
-  });
+    S.a[j] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < nn; i += nth) t.lam[b0 + i] = S.a[i];
+  for (int k = tid; k < ns; k += nth) buf[k] = S.a[t.top_sh_pos[k]];
 }
 
 // lam = r/d + gd * lam(parent); parents outside the chunk (top chunk) are read through L2
@@ -616,10 +756,9 @@ __host__ __device__ constexpr size_t tree_smem_bytes_fs(int cap) {
 
 // wait_ticket (top chunk in its own block): the chunk's own values are staged first, then the block
 // waits until all wait_count bottom blocks have published their roots.
-// pc (top chunk, multi-GPU): after this rank's bottom-chunk children are folded in, the partial pivots /
-// link conductances / right-hand sides of the replicated top chunk are exchanged with the other ranks
-// over NVLink (peer_allgather) and added up in rank order; every rank then eliminates the identical
-// top chunk.
+// pc (top chunk, multi-GPU): the partial sums of the SHARED nodes are exchanged with the other ranks inside
+// the kernel, see the body.
+template <bool DIST = false>
 __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem& S, double* __restrict__ Se,
                                                 const ChunkInfo& ci, bool top, const FusedN1& f,
                                                 unsigned int* wait_ticket = nullptr, int wait_count = 0,
@@ -662,38 +801,88 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
     }
     __syncthreads();
     NXFX_STAMP(top, 5);
-    if (pc && pc->nranks > 1) {
-      peer_allgather(*pc, 0, 3 * nn, [&](int i) { return i < nn ? S.b[i] : (i < 2 * nn ? Se[i - nn] : S.a[i - 2 * nn]); });
-      for (int i = tid; i < nn; i += nth) {
-        double ad = 0.0, tg = 0.0, ar = 0.0;
-        for (int src = 0; src < pc->nranks; ++src) {
-          const double* d = peer_data(*pc, pc->rank, 0, src);
-          ad += __ldcg(d + i);
-          tg += __ldcg(d + nn + i);
-          ar += __ldcg(d + 2 * nn + i);
-        }
-        S.b[i] = ad;
-        Se[i] = tg;
-        S.a[i] = ar;
-      }
-      __syncthreads();
-    }
   }
-  sweep_up(S, ci, [&](int n) {
-    const int i = n - b0;
-    double ad = S.b[i], ar = S.a[i];
-    for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
-      const int c = S.cidx[k] - b0;
-      if (c >= 0) {
-        ad -= Se[c] * S.c[c];
-        ar += S.c[c] * S.a[c];
+  // per-node elimination (factor + forward solve); the shared nodes of a partitioned network take only their
+  // SHARED children here -- their private children were folded into the exchanged partial sums
+  auto eliminate = [&](bool shared_children_only) {
+    return [&, shared_children_only](int n) {
+      const int i = n - b0;
+      double ad = S.b[i], ar = S.a[i];
+      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+        const int c = S.cidx[k] - b0;
+        if (c >= 0 && (!shared_children_only || tree_shared(S, c))) {
+          ad -= Se[c] * S.c[c];
+          ar += S.c[c] * S.a[c];
+        }
       }
+      const double inv = 1.0 / ad;
+      S.b[i] = inv;
+      S.c[i] = Se[i] * inv;
+      S.a[i] = ar;
+    };
+  };
+  const bool multi = DIST && top && pc && pc->nranks > 1 && t.n_sh > 0;
+  if (!multi) {
+    // single GPU / bottom chunks: the plain level sweep (the latency-critical loop carries nothing else)
+    sweep_up(S, ci, [&](int n) {
+      const int i = n - b0;
+      double ad = S.b[i], ar = S.a[i];
+      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+        const int c = S.cidx[k] - b0;
+        if (c >= 0) {
+          ad -= Se[c] * S.c[c];
+          ar += S.c[c] * S.a[c];
+        }
+      }
+      const double inv = 1.0 / ad;
+      S.b[i] = inv;
+      S.c[i] = Se[i] * inv;
+      S.a[i] = ar;
+    });
+  } else {
+    // Partitioned network.  The top chunk holds this rank's PRIVATE heavy nodes (complete locally) and the
+    // SHARED ones (replicated).  (1) eliminate the private nodes; (2) fold them into their shared parents;
+    // (3) exchange [partial pivot | link conductance | partial rhs] of the shared nodes with the other ranks
+    // over NVLink and add them up in rank order; (4) eliminate the shared nodes -- identically on every rank.
+    const int ns = t.n_sh;
+    const int32_t* __restrict__ pos = t.top_sh_pos;
+    load_shared_flags(t, ci, S);
+    sweep_up_sel(S, ci, eliminate(false), kPrivateNodes, t.pr_lmin, 1 << 30);
+    for (int k = tid; k < ns; k += nth) {
+      const int j = pos[k];
+      double ad = S.b[j], ar = S.a[j];
+      for (int q = S.cptr[j]; q < S.cptr[j + 1]; ++q) {
+        const int c = S.cidx[q] - b0;
+        if (c >= 0 && !tree_shared(S, c)) {
+          ad -= Se[c] * S.c[c];
+          ar += S.c[c] * S.a[c];
+        }
+      }
+      S.b[j] = ad;
+      S.a[j] = ar;
     }
-    const double inv = 1.0 / ad;
-    S.b[i] = inv;
-    S.c[i] = Se[i] * inv;
-    S.a[i] = ar;
-  });
+    __syncthreads();
+    NXFX_STAMP(top, 12);
+    peer_ll_send(*pc, 0, 3 * ns, [&](int i) {
+      return i < ns ? S.b[pos[i]] : (i < 2 * ns ? Se[pos[i - ns]] : S.a[pos[i - 2 * ns]]);
+    });
+    __syncthreads();  // the partial sums have been read out of shared memory: they may be overwritten
+    for (int k = tid; k < ns; k += nth) {
+      double ad = 0.0, tg = 0.0, ar = 0.0;
+      for (int src = 0; src < pc->nranks; ++src) {  // rank order: the same sums on every rank
+        ad += peer_ll_recv(*pc, 0, src, k);
+        tg += peer_ll_recv(*pc, 0, src, ns + k);
+        ar += peer_ll_recv(*pc, 0, src, 2 * ns + k);
+      }
+      const int j = pos[k];
+      S.b[j] = ad;
+      Se[j] = tg;
+      S.a[j] = ar;
+    }
+    __syncthreads();
+    NXFX_STAMP(top, 13);
+    sweep_up_sel(S, ci, eliminate(true), kSharedNodes, 0, t.sh_lmax);
+  }
   NXFX_STAMP(top, 6);
   for (int i = tid; i < nn; i += nth) { t.d[b0 + i] = S.b[i]; t.gd[b0 + i] = S.c[i]; }
   NXFX_STAMP(top, 7);
@@ -703,6 +892,7 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
 // stages the chunk's own diagonals / right-hand sides while the bottom blocks work, waits for their
 // roots (ticket), factorises + solves the top chunk and raises the epoch flag; the bottom blocks
 // then back-substitute their chunk straight from shared memory.
+template <bool DIST>
 __global__ void __launch_bounds__(kTreeThreads, 2)
 tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch,
                               FusedN1 fin, PeerDev pc) {
@@ -721,7 +911,7 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
   asm volatile("griddepcontrol.launch_dependents;");
   NXFX_STAMP(is_top, 2);
   if (is_top) {
-    factor_solve_up(t, S, Se, ci, true, fin, ticket, n_bottom, &pc);
+    factor_solve_up<DIST>(t, S, Se, ci, true, fin, ticket, n_bottom, &pc);
     solve_down(t, S, ci, true);
     NXFX_STAMP(true, 10);
     __threadfence();
@@ -734,6 +924,7 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
     NXFX_STAMP(true, 11);
     return;
   }
+  if (DIST) fin.lam_weight = nullptr;  // only shared multipliers (top chunk) carry a weight other than 1
   factor_solve_up(t, S, Se, ci, false, fin);
   // publish the eliminated right-hand sides of the chunk roots for the top chunk
   for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x)
@@ -766,8 +957,8 @@ tree_factor_solve_bottom_kernel(TreeDev t, FusedN1 fin) {
 }
 
 // ... and the replicated top chunk in two phases around the caller's SUM all-reduce of
-// buf = [partial d | tg | partial rhs] (3 nn doubles): kPartial folds in this rank's bottom-chunk
-// children, kFinish factorises, eliminates and back-substitutes from the reduced values.
+// buf = [partial d | tg | partial rhs] of the SHARED nodes (3 n_sh doubles): kPartial folds in this rank's
+// bottom-chunk children, kFinish factorises, eliminates and back-substitutes from the reduced values.
 template <int PHASE>
 __global__ void __launch_bounds__(kTreeThreads)
 tree_top_fs_kernel(TreeDev t, int top_chunk, double* buf, FusedN1 fin) {
@@ -776,7 +967,27 @@ tree_top_fs_kernel(TreeDev t, int top_chunk, double* buf, FusedN1 fin) {
   double* Se = reinterpret_cast<double*>(tree_smem_raw + ((tree_smem_bytes(t.cap) + 15) & ~(size_t)15));
   const ChunkInfo ci = load_chunk_info(t, top_chunk, S);
   const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
+  const int ns = t.n_sh;
+  const int32_t* __restrict__ pos = t.top_sh_pos;
   load_children(t, ci, S);
+  load_shared_flags(t, ci, S);
+  auto eliminate = [&](bool shared_children_only) {
+    return [&, shared_children_only](int n) {
+      const int i = n - b0;
+      double ad = S.b[i], ar = S.a[i];
+      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+        const int c = S.cidx[k] - b0;
+        if (c >= 0 && (!shared_children_only || tree_shared(S, c))) {
+          ad -= Se[c] * S.c[c];
+          ar += S.c[c] * S.a[c];
+        }
+      }
+      const double inv = 1.0 / ad;
+      S.b[i] = inv;
+      S.c[i] = Se[i] * inv;
+      S.a[i] = ar;
+    };
+  };
   if (PHASE == kPartial) {
     for (int i = tid; i < nn; i += nth) {
       const int pe = t.t_pslot[b0 + i];
@@ -785,7 +996,7 @@ tree_top_fs_kernel(TreeDev t, int top_chunk, double* buf, FusedN1 fin) {
       Se[i] = pe >= 0 ? 1.0 / fin.cell_rh[pe] : 0.0;
     }
     __syncthreads();
-    for (int i = tid; i < nn; i += nth) {
+    for (int i = tid; i < nn; i += nth) {  // this rank's bottom-chunk children
       double ad = S.b[i], ar = S.a[i];
       for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
         const int c = S.cidx[k];
@@ -794,36 +1005,59 @@ tree_top_fs_kernel(TreeDev t, int top_chunk, double* buf, FusedN1 fin) {
           ar += t.gd[c] * t.r[c];
         }
       }
-      buf[i] = ad;
-      buf[nn + i] = Se[i];
-      buf[2 * nn + i] = ar;
+      S.b[i] = ad;
+      S.a[i] = ar;
+    }
+    __syncthreads();
+    sweep_up_sel(S, ci, eliminate(false), kPrivateNodes, t.pr_lmin, 1 << 30);  // the nodes private to this rank are complete
+    for (int k = tid; k < ns; k += nth) {              // ... and fold into their shared parents
+      const int j = pos[k];
+      double ad = S.b[j], ar = S.a[j];
+      for (int q = S.cptr[j]; q < S.cptr[j + 1]; ++q) {
+        const int c = S.cidx[q] - b0;
+        if (c >= 0 && !tree_shared(S, c)) {
+          ad -= Se[c] * S.c[c];
+          ar += S.c[c] * S.a[c];
+        }
+      }
+      S.b[j] = ad;
+      S.a[j] = ar;
+    }
+    __syncthreads();
+    for (int i = tid; i < nn; i += nth) {  // scratch (arrays kFinish overwrites anyway)
+      t.d[b0 + i] = S.b[i];                       // private: 1/d (final); shared: partial pivot
+      t.gd[b0 + i] = tree_shared(S, i) ? Se[i] : S.c[i];   // private: gd (final); shared: link conductance
+      t.lam[b0 + i] = S.a[i];                     // eliminated / partial right-hand side
+    }
+    for (int k = tid; k < ns; k += nth) {  // the shared ones go to the all-reduce
+      const int j = pos[k];
+      buf[k] = S.b[j];
+      buf[ns + k] = Se[j];
+      buf[2 * ns + k] = S.a[j];
     }
   } else {
-  for (int i = tid; i < nn; i += nth) {
-    S.b[i] = buf[i];
-    Se[i] = buf[nn + i];
-    S.a[i] = buf[2 * nn + i];
-    S.par[i] = t.t_parent[b0 + i];
-    t.tg[b0 + i] = Se[i];  // all-reduced link conductances
-  }
-  __syncthreads();
-  sweep_up(S, ci, [&](int n) {
-    const int i = n - b0;
-    double ad = S.b[i], ar = S.a[i];
-    for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
-      const int c = S.cidx[k] - b0;
-      if (c >= 0) {
-        ad -= Se[c] * S.c[c];
-        ar += S.c[c] * S.a[c];
-      }
+    for (int i = tid; i < nn; i += nth) {
+      S.b[i] = t.d[b0 + i];
+      S.c[i] = t.gd[b0 + i];
+      S.a[i] = t.lam[b0 + i];
+      Se[i] = 0.0;
+      S.par[i] = t.t_parent[b0 + i];
     }
-    const double inv = 1.0 / ad;
-    S.b[i] = inv;
-    S.c[i] = Se[i] * inv;
-    S.a[i] = ar;
-  });
-  for (int i = tid; i < nn; i += nth) { t.d[b0 + i] = S.b[i]; t.gd[b0 + i] = S.c[i]; }
-  solve_down(t, S, ci, true);
+    __syncthreads();
+    for (int k = tid; k < ns; k += nth) {
+      const int j = pos[k];
+      S.b[j] = buf[k];
+      Se[j] = buf[ns + k];
+      S.a[j] = buf[2 * ns + k];
+    }
+    __syncthreads();
+    sweep_up_sel(S, ci, eliminate(true), kSharedNodes, 0, t.sh_lmax);
+    for (int k = tid; k < ns; k += nth) {
+      const int j = pos[k];
+      t.d[b0 + j] = S.b[j];
+      t.gd[b0 + j] = S.c[j];
+    }
+    solve_down(t, S, ci, true);
   }
 }
 

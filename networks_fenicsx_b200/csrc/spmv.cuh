@@ -324,12 +324,12 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
     double mine[2] = {block_sum<kTileRows>(nrm, red), block_sum<kTileRows>(nrb, red)};
     if (!finish_partials<kTileRows, 2>(mine, partial, gridDim.x, ticket, loc, red)) return;
     __syncthreads();  // loc[] written by thread 0
-    peer_allgather(pc, 1, n_shared + 2,
-                   [&](int i) { return i < n_shared ? __ldcg(lam_scratch + shared_lm[i]) : loc[i - n_shared]; });
+    peer_ll_send(pc, 1, n_shared + 2,
+                 [&](int i) { return i < n_shared ? __ldcg(lam_scratch + shared_lm[i]) : loc[i - n_shared]; });
     double acc = 0.0;
     for (int i = tid; i < n_shared; i += kTileRows) {
       double v = 0.0;
-      for (int src = 0; src < pc.nranks; ++src) v += __ldcg(peer_data(pc, pc.rank, 1, src) + i);
+      for (int src = 0; src < pc.nranks; ++src) v += peer_ll_recv(pc, 1, src, i);  // rank order
       if (y) y[loff + shared_lm[i]] = v;
       acc += v * v;
     }
@@ -337,9 +337,8 @@ spmv_pipe_kernel(int n, int ntiles, const int32_t* __restrict__ rowptr,
     if (tid == 0) {
       double s0 = acc, s1 = 0.0;
       for (int src = 0; src < pc.nranks; ++src) {
-        const double* d = peer_data(pc, pc.rank, 1, src);
-        s0 += __ldcg(d + n_shared);
-        s1 += __ldcg(d + n_shared + 1);
+        s0 += peer_ll_recv(pc, 1, src, n_shared);
+        s1 += peer_ll_recv(pc, 1, src, n_shared + 1);
       }
       norm2_out[0] = s0;
       norm2_out[1] = s1;

@@ -35,10 +35,10 @@ class TreePartition:
     global_nodes: np.ndarray  # local node -> global node
     global_edges: np.ndarray  # local edge -> global edge
     global_bif: np.ndarray  # local multiplier -> global multiplier index
-    shared_lm: np.ndarray  # local multiplier indices of the replicated (top-chunk) multipliers
+    shared_lm: np.ndarray  # local multiplier indices of the replicated (shared) multipliers
     lam_weight: np.ndarray  # 1.0 where this rank counts the multiplier row in norms / -r_lambda
-    schedule: TreeSchedule  # local elimination schedule, top chunk (identical on all ranks) last
-    n_top: int
+    schedule: TreeSchedule  # local elimination schedule; top chunk (this rank's private heavy nodes + the shared ones) last
+    n_top: int  # number of SHARED multipliers (the exchanged part of the top chunk), identical on all ranks
     n_global_bif: int
 
 
@@ -69,7 +69,23 @@ def partition_tree(graph: ArrayGraph, world: int, rank: int, chunk_nodes: int = 
         raise ValueError(f"network too small to cut into {world} parts")
     top = chunk == n_bottom
     rank_of_chunk = (np.arange(n_bottom) * world) // n_bottom
-    owner_bif = np.where(top, 0, rank_of_chunk[np.minimum(chunk, n_bottom - 1)])  # top edges -> rank 0
+    # Heavy (top-chunk) nodes come in two kinds.  A heavy node all of whose bottom chunks went to ONE rank is
+    # PRIVATE to that rank: it joins that rank's top chunk and nobody else sees it.  Only the heavy nodes
+    # whose subtree spans several ranks are SHARED (replicated, exchanged): world - 1 nodes for a balanced
+    # binary tree instead of the whole top of the elimination tree (7 instead of 2047 on 8 GPUs), so the
+    # redundant top-chunk work and the exchanged payload stay constant as the number of GPUs grows.
+    rmin = np.full(n_bif, world, dtype=np.int64)
+    rmax = np.full(n_bif, -1, dtype=np.int64)
+    rmin[~top] = rmax[~top] = rank_of_chunk[chunk[~top]]
+    by_depth = np.argsort(depth, kind="stable")
+    bounds = np.flatnonzero(np.diff(depth[by_depth])) + 1
+    for lv in reversed(np.split(by_depth, bounds)):
+        lv = lv[parent[lv] >= 0]
+        np.minimum.at(rmin, parent[lv], rmin[lv])
+        np.maximum.at(rmax, parent[lv], rmax[lv])
+    shared_bif = top & (rmin != rmax)
+    # shared nodes (and the edges between two of them) -> rank 0; private heavy nodes -> their rank
+    owner_bif = np.where(shared_bif, 0, np.where(top, rmin, rank_of_chunk[np.minimum(chunk, n_bottom - 1)]))
     # every edge follows its deeper bifurcation
     a, b = lm[u], lm[v]
     da = np.where(a >= 0, depth[np.maximum(a, 0)], -1)
@@ -77,8 +93,8 @@ def partition_tree(graph: ArrayGraph, world: int, rank: int, chunk_nodes: int = 
     deeper = np.where(db >= da, b, a)
     owner_edge = np.where(deeper >= 0, owner_bif[np.maximum(deeper, 0)], 0)
     ge = np.flatnonzero(owner_edge == rank)
-    # local nodes: endpoints of the local edges and ALL cut (top-chunk) nodes, ascending global id
-    gn = np.unique(np.concatenate([edges[ge].ravel(), bif[top]]))
+    # local nodes: endpoints of the local edges and ALL shared nodes, ascending global id
+    gn = np.unique(np.concatenate([edges[ge].ravel(), bif[shared_bif]]))
     local_of = np.full(n_nodes, -1, dtype=np.int64)
     local_of[gn] = np.arange(gn.size)
     attrs = {k: np.asarray(val)[ge] for k, val in graph.edge_attrs.items()}
@@ -88,7 +104,7 @@ def partition_tree(graph: ArrayGraph, world: int, rank: int, chunk_nodes: int = 
     gb = lm[lbif_nodes]  # global multiplier index of every local multiplier
     lb_of_gb = np.full(n_bif, -1, dtype=np.int64)
     lb_of_gb[gb] = np.arange(gb.size)
-    mine = top[gb] | (owner_bif[gb] == rank)
+    mine = shared_bif[gb] | (owner_bif[gb] == rank)
     if not np.all(mine):
         # a bifurcation of another rank's chunk can only appear here as the far end of one of our
         # edges, which the "deeper bifurcation" rule excludes on forests
@@ -106,10 +122,10 @@ def partition_tree(graph: ArrayGraph, world: int, rank: int, chunk_nodes: int = 
     lchunk = lchunk_of[chunk[gb]]
     assert np.all(lchunk >= 0)
     sched = assemble_schedule(lpar, lpedge, depth[gb], lchunk, my_chunks.size + 1, np.zeros(0, dtype=np.int32))
-    shared = np.flatnonzero(top[gb])
-    weight = np.where(top[gb] & (rank != 0), 0.0, 1.0)
+    shared = np.flatnonzero(shared_bif[gb])
+    weight = np.where(shared_bif[gb] & (rank != 0), 0.0, 1.0)
     return TreePartition(rank, world, sub, degree[gn], gn, ge, gb, shared.astype(np.int32), weight, sched,
-                         int(top.sum()), n_bif)
+                         int(shared_bif.sum()), n_bif)
 
 
 class DistributedSolver:
@@ -306,11 +322,15 @@ class DistributedSolver:
         from . import _lib
 
         C = self._C
-        opts = self.solver.solve_options()
-        opts.ksp_type, opts.pc_type = _lib.KSP_PREONLY, _lib.PC_NETWORK_SCHUR
-        opts.refine_steps, opts.final_residual, opts.refine_rtol = int(refine_steps), int(bool(final_residual)), float(refine_rtol)
-        opts.error_if_not_converged = 0
-        info = _lib.SolveInfo()
+        key = (int(refine_steps), bool(final_residual), float(refine_rtol))
+        cache = getattr(self, "_peer_opts", None)
+        if cache is None or cache[0] != key:  # the option struct is built once: the step loop stays off the Python heap
+            opts = self.solver.solve_options()
+            opts.ksp_type, opts.pc_type = _lib.KSP_PREONLY, _lib.PC_NETWORK_SCHUR
+            opts.refine_steps, opts.final_residual, opts.refine_rtol = key[0], int(key[1]), key[2]
+            opts.error_if_not_converged = 0
+            self._peer_opts = cache = (key, opts, _lib.SolveInfo())
+        _, opts, info = cache
         self.solver.A._materialise_zero()
         self.solver.A.bind()
         self.dev.call("nxfx_solve", b, x, C.byref(opts), C.byref(info))

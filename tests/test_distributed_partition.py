@@ -45,7 +45,7 @@ def test_partitioned_assembly_sums_to_global(case, world, N, chunk):
     S = sp.csr_matrix(A.shape)
     bsum = np.zeros_like(b)
     edge_seen = np.zeros(G.number_of_edges(), dtype=int)
-    top_orders = []
+    top_orders, private = [], []
     for rank in range(world):
         part = partition_tree(G, world, rank, chunk_nodes=chunk)
         edge_seen[part.global_edges] += 1
@@ -62,17 +62,25 @@ def test_partitioned_assembly_sums_to_global(case, world, N, chunk):
         s = part.schedule
         t0 = s.lvl_ptr[s.chunk_lptr[-2]]
         bif_of_t = np.argsort(s.t_of_bif)
-        top_orders.append(part.global_bif[bif_of_t[t0:]].tolist())
-        assert len(top_orders[-1]) == part.n_top == part.shared_lm.size
-        assert sorted(part.global_bif[part.shared_lm].tolist()) == sorted(top_orders[-1])
+        top_nodes = part.global_bif[bif_of_t[t0:]].tolist()
+        shared_global = part.global_bif[part.shared_lm].tolist()
+        top_orders.append(shared_global)  # exchanged in THIS order: must be the same on every rank
+        private.append(sorted(set(top_nodes) - set(shared_global)))
+        assert part.n_top == part.shared_lm.size and set(shared_global) <= set(top_nodes)
         assert np.all(part.lam_weight[part.shared_lm] == (1.0 if rank == 0 else 0.0))
+        assert np.all(np.delete(part.lam_weight, part.shared_lm) == 1.0)
         for t in range(s.t_parent.size):  # tree links stay inside the part
             if s.t_parent[t] >= 0 and s.t_pedge[t] >= 0:
                 u, v = part.graph.edges[s.t_pedge[t]]
                 gu, gv = part.global_nodes[u], part.global_nodes[v]
                 assert {gnet.lm_index[gu], gnet.lm_index[gv]} == {part.global_bif[bif_of_t[t]], part.global_bif[bif_of_t[s.t_parent[t]]]}
     assert np.all(edge_seen == 1), "every graph edge belongs to exactly one rank"
-    assert all(o == top_orders[0] for o in top_orders), "top chunk order differs between ranks"
+    assert all(o == top_orders[0] for o in top_orders), "the shared multipliers (or their order) differ between ranks"
+    # heavy nodes whose subtree stays on one rank are private to it: nobody else holds them
+    allp = [n for p in private for n in p]
+    assert len(allp) == len(set(allp)) and not set(allp) & set(top_orders[0])
+    if case.startswith("tree"):  # balanced binary tree, chunks dealt in order: only the nodes above the rank subtrees are shared
+        assert len(top_orders[0]) == world - 1
     assert abs(S - A).max() < 1e-14
     S.eliminate_zeros()
     np.testing.assert_allclose(bsum, b, rtol=0, atol=1e-14)
