@@ -407,15 +407,15 @@ int do_pc_setup(nxfx_ctx* ctx) {
   return NXFX_OK;
 }
 
-// factorisation and first application z = P^{-1} r in one cooperative launch (N == 1, single GPU)
+// factorisation and first application z = P^{-1} r in one cooperative launch
 bool can_fuse_setup(const nxfx_ctx* ctx) {
-  return ctx->N == 1 && ctx->tree.set && ctx->tree.fast_ok && ctx->tree.coop_fs_ok && ctx->n_bif > 0 &&
+  return ctx->tree.set && ctx->tree.fast_ok && ctx->tree.coop_fs_ok && ctx->n_bif > 0 &&
          ctx->tree.n_chunks > 1 && (!ctx->lam_weight.p || ctx->comm.ready) && ctx->cur->acc_count == 1;
 }
 
 int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z, bool add = false) {
   NXFX_REQUIRE(ctx, is_assembled(ctx), "assemble the matrix before pc_setup");
-  NXFX_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(r) & 15) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0,
+  NXFX_REQUIRE(ctx, ctx->N != 1 || ((reinterpret_cast<uintptr_t>(r) & 15) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0),
                "vectors must be 16-byte aligned");
   auto& s = ctx->tree;
   Net g = make_net(ctx);
@@ -426,6 +426,20 @@ int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z, bool add = fals
   unsigned int ep = ++s.epoch;
   int nb = s.n_chunks - 1;
   PeerDev pc = make_peer(ctx, 0);  // multi-GPU: the top block exchanges its partial sums with the peers
+  const bool n1 = ctx->N == 1;
+  if (!n1) {
+    // several cells per edge: the per-edge condensation and the bifurcation sums are separate streaming
+    // kernels; the tree kernel then stages the node arrays (diag0, tg, r) instead of the incidence table
+    NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N,
+                ctx->cur->cell_rh.p, ctx->edge_g.p);
+    NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, ctx->edge_g.p);
+    NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cur->cell_rh.p, r,
+                ctx->edge_c.p, ctx->edge_fn.p);
+    NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->edge_g.p,
+                ctx->edge_c.p, ctx->edge_fn.p, ctx->lam_weight.p);
+    fin.r = nullptr;
+    fin.cell_rh = nullptr;
+  }
   // both kernels are programmatic dependents of their predecessor: the tree kernel stages its
   // schedule tables while the assembly drains, the back-substitution its edge data while the tree
   // kernel finishes (cooperative + programmatic launch; plain cooperative launch if refused)
@@ -459,6 +473,12 @@ int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z, bool add = fals
   bc.stream = ctx->stream;
   bc.attrs = attr + 1;
   bc.numAttrs = 1;
+  if (!n1) {  // (the general back-substitution has no programmatic-dependency wait: plain launch)
+    const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
+    if (add) NXFX_LAUNCH(ctx, edge_backsub_kernel<true>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+    else NXFX_LAUNCH(ctx, edge_backsub_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, ctx->edge_g.p, ctx->edge_c.p, z);
+    return NXFX_OK;
+  }
   if (add) NXFX_CUDA(ctx, cudaLaunchKernelEx(&bc, edge_backsub_n1_kernel<true>, g, t, (const double*)ctx->cur->cell_rh.p, r, z));
   else NXFX_CUDA(ctx, cudaLaunchKernelEx(&bc, edge_backsub_n1_kernel<false>, g, t, (const double*)ctx->cur->cell_rh.p, r, z));
   ctx->launches++;
@@ -501,7 +521,7 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
     // partitioned network: the stored factors of the top chunk are not kept per rank; re-eliminate with
     // the fused kernel (same cost as a solve: the sweeps are latency-bound) and exchange over NVLink
     NXFX_REQUIRE(ctx, pc_type == NXFX_PC_NETWORK_SCHUR && can_fuse_setup(ctx),
-                 "the fused partitioned solve needs one cell per edge, a forest schedule that fits the cooperative kernel and pc_type lu");
+                 "the fused partitioned solve needs a forest schedule that fits the cooperative kernel and pc_type lu");
     return do_pc_setup_apply(ctx, r, z, add);
   }
   if (pc_type == NXFX_PC_NONE) {
@@ -1237,7 +1257,7 @@ int nxfx_solve(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts*
   bool fused_setup = false;
   if (ctx->comm.ready)
     NXFX_REQUIRE(ctx, can_fuse_setup(ctx) || (ctx->pc_ready && ctx->cur->acc_count == 1),
-                 "the fused partitioned solve needs one cell per edge and a forest schedule that fits the cooperative kernel");
+                 "the fused partitioned solve needs a forest schedule that fits the cooperative kernel");
   if (opts->pc_type == NXFX_PC_NETWORK_SCHUR && !ctx->pc_ready) {
     // a fresh matrix and a direct solve: factorise while eliminating the right-hand side
     fused_setup = opts->ksp_type == NXFX_KSP_PREONLY && can_fuse_setup(ctx);
@@ -1547,9 +1567,9 @@ int nxfx_comm_create(nxfx_ctx* ctx, int32_t rank, int32_t nranks, void* handle_o
   NXFX_REQUIRE(ctx, nranks >= 2 && nranks <= kMaxPeers && rank >= 0 && rank < nranks, "bad rank / nranks");
   NXFX_REQUIRE(ctx, ctx->tree.set && ctx->lam_nonshared.p, "call nxfx_set_tree_schedule and nxfx_set_shared first");
   // the exchange lives in the fused cooperative tree kernel: one cell per edge, all chunks of this rank co-resident
-  if (!(ctx->N == 1 && ctx->tree.fast_ok && ctx->tree.coop_fs_ok && ctx->tree.n_chunks > 1 && ctx->pipe_ok))
-    return fail(ctx, NXFX_ERR_UNSUPPORTED, "the in-kernel exchange needs one cell per edge and a schedule whose %d chunks fit "
-                "the cooperative tree kernel at once; use the split phases (nxfx_pc_*_begin/_end) instead", ctx->tree.n_chunks);
+  if (!(ctx->tree.fast_ok && ctx->tree.coop_fs_ok && ctx->tree.n_chunks > 1 && ctx->pipe_ok))
+    return fail(ctx, NXFX_ERR_UNSUPPORTED, "the in-kernel exchange needs a schedule whose %d chunks fit the cooperative tree "
+                "kernel at once; use the split phases (nxfx_pc_*_begin/_end) instead", ctx->tree.n_chunks);
   static_assert(sizeof(cudaIpcMemHandle_t) == NXFX_COMM_HANDLE_BYTES, "handle size");
   nxfx_comm_destroy(ctx);
   PeerComm& c = ctx->comm;

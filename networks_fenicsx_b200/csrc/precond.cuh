@@ -764,16 +764,25 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
                                                 unsigned int* wait_ticket = nullptr, int wait_count = 0,
                                                 const PeerDev* pc = nullptr) {
   const int b0 = ci.b0, nn = ci.b1 - ci.b0, tid = threadIdx.x, nth = blockDim.x;
-  for (int i = tid; i < nn; i += nth) {
-    double dg;
-    S.a[i] = n1_node_rhs_diag(f, t, b0 + i, dg);
-    S.b[i] = dg;
-    const int pe = t.t_pslot[b0 + i];
-    const double tg = pe >= 0 ? 1.0 / f.cell_rh[pe] : 0.0;
-    Se[i] = tg;
-    const int p = t.t_parent[b0 + i];
-    S.par[i] = p;
-    if (p < b0 || p >= ci.b1) t.tg[b0 + i] = tg;  // chunk roots: read by the top chunk
+  if (f.cell_rh) {  // one cell per edge: diagonals / right-hand sides straight from (r, R h)
+    for (int i = tid; i < nn; i += nth) {
+      double dg;
+      S.a[i] = n1_node_rhs_diag(f, t, b0 + i, dg);
+      S.b[i] = dg;
+      const int pe = t.t_pslot[b0 + i];
+      const double tg = pe >= 0 ? 1.0 / f.cell_rh[pe] : 0.0;
+      Se[i] = tg;
+      const int p = t.t_parent[b0 + i];
+      S.par[i] = p;
+      if (p < b0 || p >= ci.b1) t.tg[b0 + i] = tg;  // chunk roots: read by the top chunk
+    }
+  } else {  // several cells per edge: the node arrays were filled by bif_diag_kernel / bif_rhs_kernel
+    for (int i = tid; i < nn; i += nth) {
+      S.a[i] = t.r[b0 + i];
+      S.b[i] = t.diag0[b0 + i];
+      Se[i] = t.tg[b0 + i];
+      S.par[i] = t.t_parent[b0 + i];
+    }
   }
   __syncthreads();
   NXFX_STAMP(top, 3);

@@ -140,7 +140,8 @@ class DistributedSolver:
             the GLOBAL network (per graph edge or per cell) and restricted to the local edges here.
         exchange: ``"peer"``: the kernels exchange the partial sums themselves over NVLink (CUDA IPC peer
             memory, ``peer.cuh``) -- the single-GPU launch sequence, no NCCL call, one host sync per solve
-            (needs ``N == 1``); ``"nccl"``: split phases around ``torch.distributed`` all-reduces;
+            (needs every chunk of this rank co-resident in the cooperative tree kernel: up to ~21 generations
+            per GPU); ``"nccl"``: split phases around ``torch.distributed`` all-reduces;
             ``"auto"``: peer when available.
         device: CUDA ordinal of this rank.
     """
@@ -204,10 +205,8 @@ class DistributedSolver:
         self.exchange = "nccl"
         if exchange not in ("auto", "peer", "nccl"):
             raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
-        if exchange != "nccl" and N == 1:
+        if exchange != "nccl":
             self._connect_peers(required=exchange == "peer")
-        elif exchange == "peer":
-            raise ValueError("exchange='peer' (fused kernels with in-kernel NVLink exchange) needs N == 1")
 
     def _connect_peers(self, required: bool) -> None:
         """Peer exchange over NVLink (``peer.cuh``): every rank exports its exchange buffer as a CUDA IPC
