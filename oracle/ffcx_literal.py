@@ -74,3 +74,51 @@ def cell_tensors(x0, x1, flux_degree: int, pressure_degree: int, R: float = 1.0,
         B += W[g] * np.outer(psi[:, g], dq_dt) * detJ
         L += W[g] * f * psi[:, g] * detJ
     return M, B, L
+
+
+def assemble_cellwise(net, pbc_vertex, R=1.0, f=0.0):
+    """The block system of a (small) network assembled the way DOLFINx does it -- a loop over cells that
+    tabulates the element tensors by quadrature (``cell_tensors``) and adds them into a DENSE matrix through
+    the cell dof maps, then a loop over the bifurcation / boundary end-vertices for the point terms
+    (assembly.py:258-260, 268-277).  ``net`` is an ``OracleNetworkHO`` (or ``OracleNetwork`` with
+    ``fd = 1, pd = 0``): only its dof maps are used.  An independent check of the vectorised COO assembly of
+    ``reference_port.py`` and of the product's table-driven path (both multiply reference tables by R h)."""
+    fd = getattr(net, "fd", 1)
+    pd = getattr(net, "pd", 0)
+    n = net.n_dofs
+    A = np.zeros((n, n))
+    b = np.zeros(n)
+    qd = net.cell_flux_dofs() if hasattr(net, "cell_flux_dofs") else np.stack(
+        [net.fb[np.repeat(np.arange(net.E), net.N)] + np.tile(np.arange(net.N), net.E),
+         net.fb[np.repeat(np.arange(net.E), net.N)] + np.tile(np.arange(net.N), net.E) + 1], axis=1)
+    pdofs = net.cell_pressure_dofs() if hasattr(net, "cell_pressure_dofs") else (net.poff + np.arange(net.E * net.N))[:, None]
+    nc = net.cells.shape[0]
+    Rc = np.broadcast_to(np.asarray(R, dtype=np.float64), (nc,))
+    fc = np.broadcast_to(np.asarray(f, dtype=np.float64), (nc,))
+    for c in range(nc):
+        x0, x1 = net.x3[net.cells[c, 0]], net.x3[net.cells[c, 1]]
+        M, B, L = cell_tensors(x0, x1, fd, pd, R=float(Rc[c]), f=float(fc[c]), orientation=float(net.orientation[c]))
+        for a in range(fd + 1):
+            for bb in range(fd + 1):
+                A[qd[c, a], qd[c, bb]] += M[a, bb]
+            for r in range(pd + 1):
+                A[pdofs[c, r], qd[c, a]] += B[r, a]   # a[P][i] = + phi grad(q).t
+                A[qd[c, a], pdofs[c, r]] -= B[r, a]   # a[i][P] = - p grad(v).t
+        for r in range(pd + 1):
+            b[pdofs[c, r]] += L[r]
+    N = net.N
+    for e, (u, v) in enumerate(net.edges):
+        first, last = e * N, e * N + N - 1
+        if net.lm_index[v] >= 0:   # edge enters bifurcation v: + mu q and + lam v at the END vertex (local dof 1)
+            lm = net.loff + net.lm_index[v]
+            A[lm, qd[last, 1]] += 1.0
+            A[qd[last, 1], lm] += 1.0
+        else:                      # outlet: + p_bc v
+            b[qd[last, 1]] += pbc_vertex[v]
+        if net.lm_index[u] >= 0:   # edge leaves bifurcation u: - mu q and - lam v at the START vertex (local dof 0)
+            lm = net.loff + net.lm_index[u]
+            A[lm, qd[first, 0]] -= 1.0
+            A[qd[first, 0], lm] -= 1.0
+        else:                      # inlet: - p_bc v
+            b[qd[first, 0]] -= pbc_vertex[u]
+    return A, b

@@ -14,8 +14,9 @@ ROOT = pathlib.Path(__file__).resolve().parent.parent
 @pytest.mark.parametrize("args", [
     ("11", "1", "64", "tree", "peer"),       # in-kernel NVLink exchange (fused kernels)
     ("11", "1", "64", "tree", "nccl"),       # split phases around torch.distributed all-reduces
-    ("9", "4", "32", "tree", "auto"),        # refined edges: nccl path
+    ("9", "4", "32", "tree", "auto"),        # refined edges (4 cells per edge): fused kernels with array staging
     ("10", "1", "64", "arterial", "peer"),   # BASELINE configs[3]: radius-dependent R, f != 0
+    ("8", "4", "32", "arterial", "peer"),
     ("8", "4", "32", "arterial", "nccl"),
 ])
 def test_single_tree_partition_two_gpus(args):

@@ -220,3 +220,27 @@ def test_closed_form_element_tensors_equal_the_quadrature_literal(fd, pd):
     if (fd, pd) == (1, 0):
         np.testing.assert_allclose(M_ref, [[1 / 3, 1 / 6], [1 / 6, 1 / 3]], rtol=1e-15)
         np.testing.assert_allclose(B_ref, [[-1.0, 1.0]], rtol=1e-15)
+
+
+@pytest.mark.parametrize("fd,pd", [(1, 0), (2, 1), (3, 2), (2, 0)])
+def test_vectorised_assembly_equals_the_cellwise_quadrature_assembly(fd, pd):
+    """The COO assembly of the oracle (reference tables x R h, vectorised over cells) against a DOLFINx-style
+    cell loop with quadrature-tabulated element tensors and dense accumulation: values of A (explicit zeros
+    aside) and b agree to rounding on a Y bifurcation, a random tree and the cyclic test graph."""
+    from oracle import ffcx_literal
+
+    rng = np.random.default_rng(3 * fd + pd)
+    from networks_fenicsx_b200 import network_generation as ng
+
+    for G, N, strategy in ((ng.make_tree(2, 1, 3), 3, None), (helpers.random_tree(25, 5), 2, "smallest_last"),
+                           (helpers.edge_info_graph(), 2, "largest_first")):
+        coloring = rp.color_graph_literal(G, strategy)
+        pos, edges, colors = rp.graph_to_arrays(G, coloring)
+        net = rp.OracleNetworkHO(pos, edges, colors, N, fd, pd) if (fd, pd) != (1, 0) else rp.OracleNetwork(pos, edges, colors, N)
+        nc = N * edges.shape[0]
+        R, f = rng.uniform(0.5, 2.0, nc), rng.normal(size=nc)
+        pbc = net.eval_pbc(lambda x: x[1] - 0.3 * x[0])
+        A, b = net.assemble(pbc, R=R, f=f)
+        Ad, bd = ffcx_literal.assemble_cellwise(net, pbc, R=R, f=f)
+        np.testing.assert_allclose(A.toarray(), Ad, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(b, bd, rtol=1e-12, atol=1e-13)
