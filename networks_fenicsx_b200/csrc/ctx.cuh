@@ -52,7 +52,8 @@ struct TreeSchedule {
   DevBuf<double> diag0, tg, d, gd, r, lam;  // schedule order
   bool fast_ok = false;                       // every chunk fits the shared-memory sweep kernel
   bool coop_ok = false;                       // all bottom chunks can be co-resident (single-launch solve)
-  bool coop_fs_ok = false;                    // ... also with the larger buffers of the fused factor + solve
+  bool coop_fs_ok = false;                    // the fused factor + solve can be launched cooperatively
+  int coop_fs_blocks = 0;                     // ... with at most this many co-resident blocks (more chunks: several per block)
   unsigned int epoch = 0;
 };
 

@@ -444,7 +444,8 @@ int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z, bool add = fals
   // schedule tables while the assembly drains, the back-substitution its edge data while the tree
   // kernel finishes (cooperative + programmatic launch; plain cooperative launch if refused)
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nb + 1);  // the last block owns the top chunk
+  const int gb = std::min(nb, s.coop_fs_blocks - 1);  // bottom blocks (each takes ceil(nb / gb) chunks)
+  cfg.gridDim = dim3(gb + 1);                         // the last block owns the top chunk
   cfg.blockDim = dim3(kTreeThreads);
   cfg.dynamicSmemBytes = tree_smem_bytes_fs(s.cap);
   cfg.stream = ctx->stream;
@@ -455,7 +456,9 @@ int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z, bool add = fals
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ctx->pdl_coop_refused ? 1 : 2;
-  auto kern = pc.nranks > 1 ? tree_factor_solve_coop_kernel<true> : tree_factor_solve_coop_kernel<false>;
+  const bool multi = gb < nb;
+  auto kern = pc.nranks > 1 ? (multi ? tree_factor_solve_coop_kernel<true, true> : tree_factor_solve_coop_kernel<true, false>)
+                            : (multi ? tree_factor_solve_coop_kernel<false, true> : tree_factor_solve_coop_kernel<false, false>);
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, t, nb, tk, fl, ep, fin, pc);
   if (le != cudaSuccess && cfg.numAttrs == 2) {
     cudaGetLastError();
@@ -1187,13 +1190,18 @@ int nxfx_set_tree_schedule(nxfx_ctx* ctx, const int32_t* t_of_bif, const int32_t
     NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_top_fs_kernel<kFinish>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes_fs(kChunkCapMax)));
     s.coop_fs_ok = false;
     per_sm = 0;
-    if (s.coop_ok && cudaFuncSetAttribute(tree_factor_solve_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)tree_smem_bytes_fs(kChunkCapMax)) == cudaSuccess &&
-        cudaFuncSetAttribute(tree_factor_solve_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)tree_smem_bytes_fs(kChunkCapMax)) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_factor_solve_coop_kernel<true>, kTreeThreads,
-                                                      tree_smem_bytes_fs(ctx->tree.cap)) == cudaSuccess)
-      s.coop_fs_ok = n_chunks <= per_sm * ctx->sm_count;  // bottom blocks + one block for the top chunk
+    const int fs_max = (int)tree_smem_bytes_fs(kChunkCapMax);
+    if (coop &&
+        cudaFuncSetAttribute(tree_factor_solve_coop_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs_max) == cudaSuccess &&
+        cudaFuncSetAttribute(tree_factor_solve_coop_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs_max) == cudaSuccess &&
+        cudaFuncSetAttribute(tree_factor_solve_coop_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs_max) == cudaSuccess &&
+        cudaFuncSetAttribute(tree_factor_solve_coop_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs_max) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_factor_solve_coop_kernel<true, true>, kTreeThreads,
+                                                      tree_smem_bytes_fs(ctx->tree.cap)) == cudaSuccess) {
+      // bottom blocks + one block for the top chunk; with more chunks than that, several chunks per block
+      s.coop_fs_blocks = per_sm * ctx->sm_count;
+      s.coop_fs_ok = s.coop_fs_blocks >= 2;
+    }
     cudaGetLastError();
     NXFX_CUDA(ctx, cudaFuncSetAttribute(tree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));
     NXFX_CUDA(ctx, cudaFuncSetAttribute((tree_top_kernel<true, kPartial>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem_bytes(kChunkCapMax)));

@@ -901,16 +901,20 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
 // stages the chunk's own diagonals / right-hand sides while the bottom blocks work, waits for their
 // roots (ticket), factorises + solves the top chunk and raises the epoch flag; the bottom blocks
 // then back-substitute their chunk straight from shared memory.
-template <bool DIST>
+// MULTI: more bottom chunks than co-resident blocks.  Bottom block k then takes the chunks k, k + G, k + 2G, ...
+// (G = bottom blocks in the grid): every chunk but its last is written back in full (eliminated right-hand
+// sides next to the factors) and re-staged for the backward sweep; the last one stays in shared memory.
+template <bool DIST, bool MULTI>
 __global__ void __launch_bounds__(kTreeThreads, 2)
 tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, unsigned int* flag, unsigned int epoch,
                               FusedN1 fin, PeerDev pc) {
   extern __shared__ __align__(16) unsigned char tree_smem_raw[];
   TreeSmem S = tree_view(tree_smem_raw, t.cap);
   double* Se = reinterpret_cast<double*>(tree_smem_raw + ((tree_smem_bytes(t.cap) + 15) & ~(size_t)15));
-  const bool is_top = (int)blockIdx.x == n_bottom;
+  const int G = (int)gridDim.x - 1;  // bottom blocks; the last block of the grid owns the top chunk
+  const bool is_top = (int)blockIdx.x == G;
   NXFX_STAMP(is_top, 0);
-  const ChunkInfo ci = load_chunk_info(t, blockIdx.x, S);
+  const ChunkInfo ci = load_chunk_info(t, is_top ? n_bottom : (int)blockIdx.x, S);
   load_children(t, ci, S);
   NXFX_STAMP(is_top, 1);
   // programmatic dependent launch: the schedule tables above are static; everything below reads the
@@ -934,22 +938,55 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
     return;
   }
   if (DIST) fin.lam_weight = nullptr;  // only shared multipliers (top chunk) carry a weight other than 1
-  factor_solve_up(t, S, Se, ci, false, fin);
-  // publish the eliminated right-hand sides of the chunk roots for the top chunk
-  for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x)
-    if (S.par[i] < ci.b0 || S.par[i] >= ci.b1) t.r[ci.b0 + i] = S.a[i];
-  __threadfence();
-  __syncthreads();
-  NXFX_STAMP(false, 8);
+  if (!MULTI) {  // one chunk per block: it stays in shared memory from the first load to the last store
+    factor_solve_up(t, S, Se, ci, false, fin);
+    // publish the eliminated right-hand sides of the chunk roots for the top chunk
+    for (int i = threadIdx.x; i < ci.b1 - ci.b0; i += blockDim.x)
+      if (S.par[i] < ci.b0 || S.par[i] >= ci.b1) t.r[ci.b0 + i] = S.a[i];
+    __threadfence();
+    __syncthreads();
+    NXFX_STAMP(false, 8);
+    if (threadIdx.x == 0) {
+      atomicAdd(ticket, 1u);
+      while (atomicAdd(flag, 0u) != epoch) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();
+    NXFX_STAMP(false, 9);
+    solve_down(t, S, ci, false);
+    NXFX_STAMP(false, 10);
+    return;
+  }
+  int chunk = (int)blockIdx.x;
+  ChunkInfo cm = ci;
+  while (true) {
+    factor_solve_up(t, S, Se, cm, false, fin);
+    const bool more = chunk + G < n_bottom;
+    // the chunk roots for the top chunk -- and every node of a chunk that has to leave shared memory
+    for (int i = threadIdx.x; i < cm.b1 - cm.b0; i += blockDim.x)
+      if (more || S.par[i] < cm.b0 || S.par[i] >= cm.b1) t.r[cm.b0 + i] = S.a[i];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(ticket, 1u);
+    if (!more) break;
+    chunk += G;
+    cm = load_chunk_info(t, chunk, S);
+    load_children(t, cm, S);
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
-    atomicAdd(ticket, 1u);
     while (atomicAdd(flag, 0u) != epoch) __nanosleep(64);
     __threadfence();
   }
   __syncthreads();
-  NXFX_STAMP(false, 9);
-  solve_down(t, S, ci, false);
-  NXFX_STAMP(false, 10);
+  solve_down(t, S, cm, false);
+  for (int c = (int)blockIdx.x; c < chunk; c += G) {  // the chunks that were written back
+    __syncthreads();
+    const ChunkInfo cj = load_chunk_info(t, c, S);
+    load_solve_chunk(t, cj, S);
+    __syncthreads();
+    solve_down(t, S, cj, false);
+  }
 }
 
 // Multi-GPU form of the fused factor + first solve: bottom chunks only (no top chunk, no backward
