@@ -194,6 +194,12 @@ int nxfx_residual(nxfx_ctx* ctx, const double* b_d, const double* x_d, double* r
 int nxfx_solve(nxfx_ctx* ctx, const double* b_d, double* x_d, const nxfx_solve_opts* opts,
                nxfx_solve_info* info); /* synchronises before returning */
 
+/* Solution mirror: replaces the device->host side of dolfinx.fem.petsc.assign (solver.py:134) for callers
+ * that want the solution in host memory.  With a pinned x_h (nxfx_host_alloc, n_dofs doubles) set,
+ * nxfx_solve copies x into it on a side stream as soon as the (last) back-substitution is enqueued --
+ * the download overlaps the residual check -- and returns after both have finished.  NULL disables.   */
+int nxfx_set_solution_mirror(nxfx_ctx* ctx, double* x_h);
+
 /* ---- (5) end-to-end host-buffer call (bench.py "e2e") -------------------------------------- *
  * One assemble+solve step with HOST inputs and outputs: uploads node positions and p_bc vertex
  * values, regenerates the vertices, assembles, solves, downloads x.  All host pointers should be

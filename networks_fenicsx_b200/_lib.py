@@ -106,6 +106,7 @@ SIGNATURES = {
     "nxfx_solve": (
         C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SolveOpts), C.POINTER(SolveInfo)]
     ),
+    "nxfx_set_solution_mirror": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nxfx_assemble_solve_host": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.POINTER(SolveOpts),

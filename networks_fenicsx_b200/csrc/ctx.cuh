@@ -133,6 +133,10 @@ struct nxfx_ctx {
   nxfx::DevBuf<int32_t> top_sh_pos;  // [n_shared] position of every shared multiplier inside the top chunk
   nxfx::DevBuf<double> lam_weight, lam_nonshared;
   nxfx::PeerComm comm;
+  // solution mirror: pinned host copy of x that nxfx_solve fills while the residual check still runs
+  double* mirror_h = nullptr;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_x = nullptr;
   // e2e staging
   nxfx::DevBuf<double> e2e_pbc, e2e_b, e2e_x;
 };

@@ -594,6 +594,16 @@ void push_history(nxfx_solve_info* info, double v) {
 // its norms: the common case (first solve already converged) costs one SpMV and no extra launch.
 // refine_rtol = 0 forces every allowed correction.  The reported residual is the last one computed;
 // final_residual adds an evaluation after the last correction.
+// solution mirror (nxfx_set_solution_mirror): x -> pinned host memory on a side stream, ordered after what is
+// enqueued on the main stream so far -- the download of the solution overlaps the residual check
+int mirror_copy(nxfx_ctx* ctx, const double* x) {
+  if (!ctx->mirror_h) return NXFX_OK;
+  NXFX_CUDA(ctx, cudaEventRecord(ctx->ev_x, ctx->stream));
+  NXFX_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_x, 0));
+  NXFX_CUDA(ctx, cudaMemcpyAsync(ctx->mirror_h, x, (size_t)ctx->ndofs * sizeof(double), cudaMemcpyDeviceToHost, ctx->side));
+  return NXFX_OK;
+}
+
 int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts* o, nxfx_solve_info* info,
                   bool fused_setup) {
   int rc = ensure_work(ctx, 3);
@@ -601,6 +611,7 @@ int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_op
   double* r = ctx->work.p;
   const int steps = std::max(0, std::min(o->refine_steps, 32));
   if ((rc = fused_setup ? do_pc_setup_apply(ctx, b, x) : do_pc_apply(ctx, o->pc_type, b, x, false))) return rc;
+  if ((rc = mirror_copy(ctx, x))) return rc;  // almost always the final x: corrections (below) copy again
   info->iterations = 1;
   if (steps == 0 && !o->final_residual) {  // plain preconditioner application, nothing measured
     NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -624,6 +635,7 @@ int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_op
     if (applied >= steps || (good && rt > 0.0) || !std::isfinite(info->residual_norm)) break;
     if (lazy && (rc = do_residual(ctx, b, x, r, slot(ctx, 0)))) return rc;
     if ((rc = do_pc_apply(ctx, o->pc_type, r, x, true))) return rc;
+    if ((rc = mirror_copy(ctx, x))) return rc;
     ++applied;
     if (applied >= steps && !o->final_residual) break;  // residual of the iterate before the last correction
   }
@@ -769,6 +781,8 @@ int nxfx_destroy(nxfx_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->scal_h) cudaFreeHost(ctx->scal_h);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->ev_x) cudaEventDestroy(ctx->ev_x);
   nxfx_comm_destroy(ctx);
   release_matrices(ctx);
   delete ctx;
@@ -1278,6 +1292,10 @@ int nxfx_solve(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts*
   else if (opts->ksp_type == NXFX_KSP_FGMRES) rc = solve_fgmres(ctx, b, x, opts, info);
   else return fail(ctx, NXFX_ERR_UNSUPPORTED, "unknown ksp_type %d", opts->ksp_type);
   if (rc) return rc;
+  if (ctx->mirror_h) {
+    if (opts->ksp_type != NXFX_KSP_PREONLY && (rc = mirror_copy(ctx, x))) return rc;
+    NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->side));
+  }
   if (ctx->comm.ready && *ctx->comm.err_h) {
     *ctx->comm.err_h = 0;
     return fail(ctx, NXFX_ERR_COMM, "a peer rank did not deliver its part of the exchange within 4 s");
@@ -1285,6 +1303,16 @@ int nxfx_solve(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts*
   if (!info->converged && opts->error_if_not_converged)
     return fail(ctx, NXFX_ERR_NOT_CONVERGED, "linear solve did not converge: ||r|| = %.3e, ||b|| = %.3e after %d iterations",
                 info->residual_norm, info->rhs_norm, info->iterations);
+  return NXFX_OK;
+}
+
+int nxfx_set_solution_mirror(nxfx_ctx* ctx, double* x_h) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  if (x_h && !ctx->side) {
+    NXFX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    NXFX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_x, cudaEventDisableTiming));
+  }
+  ctx->mirror_h = x_h;
   return NXFX_OK;
 }
 

@@ -131,9 +131,15 @@ class Solver:
         out = []
         spaces = [*asm.flux_spaces, asm.pressure_space, asm.lm_space]
         names = [f"flux_color_{i}" for i in range(len(spaces) - 2)] + ["pressure", "global_flux"]
+        # ONE pinned buffer in block order, the functions are views into it: solve() has the library mirror x into
+        # it while the residual check still runs (nxfx_set_solution_mirror)
+        mirror = dev.pinned(asm.num_dofs)
+        off = 0
         for V, name in zip(spaces, names):
-            fn = Function(V, name=name, array=dev.pinned(V.num_dofs))
+            fn = Function(V, name=name, array=mirror[off:off + V.num_dofs])
             fn._pinned = True
+            fn._mirror = mirror
+            off += V.num_dofs
             out.append(fn)
         return out
 
@@ -228,6 +234,49 @@ class Solver:
         self.info = _lib.SolveInfo()
         self._A._materialise_zero()
         self._A.bind()
+        mirror = getattr(functions[0], "_mirror", None) if not staged else None
+        if mirror is not None and not all(getattr(fn, "_mirror", None) is mirror for fn in functions):
+            mirror = None
+        # the library fills the mirror itself wherever the solve goes through nxfx_solve
+        mirrored = mirror is not None and (self._dist is None or self._dist.exchange == "peer")
+        if mirrored:
+            dev.call("nxfx_set_solution_mirror", C.c_void_p(mirror.ctypes.data))
+        try:
+            self._run_solve(opts, dev)
+        finally:
+            if mirrored:
+                dev.call("nxfx_set_solution_mirror", None)
+        self._x.mark_device_modified()
+        # fem.petsc.assign: split the blocked vector into the functions (solver.py:134)
+        if sum(fn.x.array.size for fn in functions) != self._x.n:
+            raise ValueError("functions do not match the block layout [flux colours, pressure, multipliers]")
+        if staged:
+            if self._x_stage is None:
+                self._x_stage = dev.pinned(self._x.n)
+            self._x.d.download(self._x_stage)  # one D2H, synchronises
+            off = 0
+            for fn in functions:
+                n = fn.x.array.size
+                np.copyto(fn.x.array, self._x_stage[off:off + n])
+                off += n
+        elif mirrored:  # Solver.create_functions(): the library has already mirrored x into the views
+            pass
+        elif mirror is not None:
+            self._x.d.download(mirror)  # one D2H into the buffer behind the views, synchronises
+        else:  # caller-provided pinned arrays: D2H straight into them
+            off = 0
+            for fn in functions:
+                n = fn.x.array.size
+                if n:
+                    dev.call(
+                        "nxfx_memcpy_d2h", C.c_void_p(fn.x.array.ctypes.data),
+                        C.c_void_p(self._x.d.ptr + 8 * off), C.c_size_t(8 * n),
+                    )
+                off += n
+            dev.sync()
+        return functions
+
+    def _run_solve(self, opts, dev) -> None:
         if self._dist is not None:
             hist = self._dist.solve(refine_steps=int(opts.refine_steps), final_residual=bool(opts.final_residual),
                                     refine_rtol=float(opts.refine_rtol))
@@ -246,31 +295,6 @@ class Solver:
                 )
             finally:
                 self._record_info()
-        self._x.mark_device_modified()
-        # fem.petsc.assign: split the blocked vector into the functions (solver.py:134)
-        if sum(fn.x.array.size for fn in functions) != self._x.n:
-            raise ValueError("functions do not match the block layout [flux colours, pressure, multipliers]")
-        if staged:
-            if self._x_stage is None:
-                self._x_stage = dev.pinned(self._x.n)
-            self._x.d.download(self._x_stage)  # one D2H, synchronises
-            off = 0
-            for fn in functions:
-                n = fn.x.array.size
-                np.copyto(fn.x.array, self._x_stage[off:off + n])
-                off += n
-        else:  # caller-provided pinned arrays (Solver.create_functions): D2H straight into them
-            off = 0
-            for fn in functions:
-                n = fn.x.array.size
-                if n:
-                    dev.call(
-                        "nxfx_memcpy_d2h", C.c_void_p(fn.x.array.ctypes.data),
-                        C.c_void_p(self._x.d.ptr + 8 * off), C.c_size_t(8 * n),
-                    )
-                off += n
-            dev.sync()
-        return functions
 
     def _record_info(self):
         info = self.info

@@ -588,3 +588,28 @@ def test_two_assemblers_and_solvers_on_one_network_do_not_alias():
     asm_ho.compute_forms(p_bc_ex=P_Y)
     with pytest.raises(RuntimeError, match="second NetworkMesh"):
         nxfx.Solver(asm_ho)
+
+
+def test_solution_mirror_matches_the_staged_download():
+    """Solver.create_functions(): views into one pinned buffer that the library fills on a side stream while
+    the residual check runs (nxfx_set_solution_mirror) -- also when a refinement correction changes x after
+    the first copy, with FGMRES, and without leaking the mirror into later plain solves."""
+    G = ng.make_tree(9, 4, 5)
+    rng = np.random.default_rng(2)
+    R = 10.0 ** rng.uniform(-3, 3, G.number_of_edges() * 2)
+    for opts in ({"ksp_type": "preonly", "pc_type": "lu"},
+                 {"ksp_type": "preonly", "pc_type": "lu", "nxfx_refine_rtol": 0.0, "nxfx_refine_steps": 2},
+                 {"ksp_type": "gmres", "pc_type": "lu", "ksp_rtol": 1e-13}):
+        nm, asm, solver, sol, net, A, b = run_case(G, 2, "smallest_last", P_Y, R=R, petsc_options=opts)
+        x_staged = _x_of(sol).copy()
+        fns = solver.create_functions()
+        assert all(fn.x.array.base is not None for fn in fns)
+        solver.assemble()
+        sol2 = solver.solve(fns)
+        assert sol2 is fns
+        assert np.array_equal(_x_of(fns), x_staged)
+        assert np.array_equal(solver.x.array_r, x_staged)
+        fns[0].x.array[:] = -7.0  # a later solve without these functions must not touch the mirror
+        solver.assemble()
+        solver.solve()
+        assert np.all(fns[0].x.array == -7.0)
