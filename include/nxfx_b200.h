@@ -227,6 +227,32 @@ int nxfx_assemble_generic(nxfx_ctx* ctx, const double* R_cell_d, double R_const,
                           const double* f_cell_d, double f_const, int lhs, int rhs, int accumulate,
                           double* b_d);
 
+/* Exact condensation (direct solve) for the table-driven path: what PCLU / MUMPS does for any polynomial
+ * degree in the reference (assembly.py:121-146, solver.py:58-65).  Per graph edge the unknowns that live on
+ * the edge only (flux dofs, pressure dofs inside it, pressure of a boundary node at its end) are eliminated
+ * by a banded LU with partial pivoting; the bifurcation system with 2 x 2 blocks {P_b, lam_b} is eliminated
+ * over the schedule of nxfx_set_tree_schedule.  After this call pc_type NXFX_PC_NETWORK_SCHUR works on
+ * the generic path (exact on trees, spanning-forest approximation inside FGMRES on graphs with cycles).
+ * The tables list the entries of K_e, C_e, D_e per edge type t = (u is a bifurcation) + 2 (v is a
+ * bifurcation), concatenated over the 4 types with [5]-sized offset arrays (networks_fenicsx_b200/condense.py):
+ *   type_n[4]                      local unknowns per type (<= n_max)
+ *   loc_kind / loc_off             global dof of a local unknown: 0 flux slot*flux_dofs_per_edge+off,
+ *                                  1 pcell_base+e*pcell_stride+off, 2 interior pressure vertex off of the edge,
+ *                                  3 / 4 pressure of node u / v
+ *   k_row, k_col, k_cell, k_coef   K_e entries: coef * (R h of cell k_cell of the edge | 1 if k_cell < 0);
+ *                                  |row - col| <= kl
+ *   c_row, c_slot, c_coef          C_e (local row, nodal slot 0 P_u, 1 lam_u, 2 P_v, 3 lam_v)
+ *   d_slot, d_col, d_coef          D_e (nodal row slot, local column)
+ *   bif_node_h [n_bif]             graph node of every bifurcation                                        */
+int nxfx_set_condensation(nxfx_ctx* ctx, int32_t continuous_pressure, int32_t flux_dofs_per_edge,
+                          int32_t n_max, int32_t kl, int32_t pcell_base, int32_t pcell_stride,
+                          const int32_t* type_n_h, const int32_t* loc_ptr_h, const int32_t* loc_kind_h,
+                          const int32_t* loc_off_h, const int32_t* k_ptr_h, const int32_t* k_row_h,
+                          const int32_t* k_col_h, const int32_t* k_cell_h, const double* k_coef_h,
+                          const int32_t* c_ptr_h, const int32_t* c_row_h, const int32_t* c_slot_h,
+                          const double* c_coef_h, const int32_t* d_ptr_h, const int32_t* d_slot_h,
+                          const int32_t* d_col_h, const double* d_coef_h, const int32_t* bif_node_h);
+
 /* ---- (6) multi-GPU: one rank's part of a partitioned network ------------------------------------ *
  * Replaces what MPI does inside DOLFINx/PETSc/MUMPS at assembly.py:355-367 and solver.py:127-132
  * (stash exchange, ghost updates, distributed LU).  The ctx holds one rank's sub-network in which

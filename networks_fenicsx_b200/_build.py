@@ -10,7 +10,7 @@ import subprocess
 CSRC = pathlib.Path(__file__).parent / "csrc"
 LIB = CSRC / "libnxfx_b200.so"
 SOURCES = ["nxfx_b200.cu"]
-HEADERS = ["ctx.cuh", "assemble.cuh", "spmv.cuh", "precond.cuh", "generic.cuh", "../../include/nxfx_b200.h"]
+HEADERS = ["ctx.cuh", "assemble.cuh", "spmv.cuh", "precond.cuh", "generic.cuh", "condense.cuh", "peer.cuh", "../../include/nxfx_b200.h"]
 
 
 def nvcc_path() -> str:

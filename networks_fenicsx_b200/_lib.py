@@ -120,6 +120,11 @@ SIGNATURES = {
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p],
     ),
+    "nxfx_set_condensation": (
+        C.c_int,
+        [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p,
+         c_i32p, c_i32p, c_i32p, c_i32p, c_f64p, c_i32p, c_i32p, c_i32p, c_f64p, c_i32p, c_i32p, c_i32p, c_f64p, c_i32p],
+    ),
     "nxfx_set_shared": (C.c_int, [C.c_void_p, C.c_int32, c_i32p, c_f64p]),
     "nxfx_comm_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "nxfx_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -324,6 +324,18 @@ class HydraulicNetworkAssembler:
                     c32(g.src_id), c64(g.src_coef), c32(g.bsrc_ptr), c32(g.bsrc_id), c64(g.bsrc_coef),
                 )
                 dev.sync()
+                # analysis phase of the direct solve for these degrees (condense.py / condense.cuh)
+                from .condense import build_condensation  # noqa: PLC0415
+
+                cd = build_condensation(nm, *self._degrees)
+                t = cd.packed()
+                dev.call(
+                    "nxfx_set_condensation", int(cd.pd >= 1), cd.fd * cd.N + 1, cd.n_max, cd.kl, cd.pcell_base,
+                    cd.pcell_stride, c32(t["type_n"]), c32(t["loc_ptr"]), c32(t["loc_kind"]), c32(t["loc_off"]),
+                    c32(t["k_ptr"]), c32(t["k_row"]), c32(t["k_col"]), c32(t["k_cell"]), c64(t["k_coef"]),
+                    c32(t["c_ptr"]), c32(t["c_row"]), c32(t["c_slot"]), c64(t["c_coef"]),
+                    c32(t["d_ptr"]), c32(t["d_slot"]), c32(t["d_col"]), c64(t["d_coef"]), c32(cd.bif_node),
+                )
             self._symbolic_done = True
         nnz = C.c_int64()
         dev.call("nxfx_get_sizes", None, None, None, C.byref(nnz))

@@ -68,6 +68,16 @@ struct MatState {
   int acc_count = 0;  // number of lhs assemblies accumulated since the last zero (ADD_VALUES)
 };
 
+// Exact condensation of the table-driven (higher-order) path (condense.cuh): per-edge-type entry lists from
+// the host, per-edge banded LU factors, Schur contributions, block tree factors.
+struct Condensation {
+  bool set = false;
+  int n_max = 0, kl = 0, per_edge = 0, pcell_base = 0, pcell_stride = 0, cont = 0;
+  DevBuf<int32_t> type_n, loc_ptr, loc_kind, loc_off, k_ptr, k_row, k_col, k_cell, c_ptr, c_row, c_slot, d_ptr, d_slot,
+      d_col, bif_node, ipiv;
+  DevBuf<double> k_coef, c_coef, d_coef, band, Y, S, y0, h, bd0, bU, bL, bDinv, bG, bH, br, bz;
+};
+
 // Peer exchange of the partitioned solve (peer.cuh): this rank's exchange buffer and the mapped
 // buffers of the other ranks.
 struct PeerComm {
@@ -110,6 +120,7 @@ struct nxfx_ctx {
   bool generic = false;
   nxfx::DevBuf<int32_t> gen_src_id, gen_bptr, gen_bid;
   nxfx::DevBuf<double> gen_src_coef, gen_bcoef, gen_cell_h;
+  nxfx::Condensation cond;  // exact condensation for the generic path (nxfx_set_condensation)
   std::vector<nxfx::MatState*> mats;  // every matrix created on the current pattern ([0] = default)
   nxfx::MatState* cur = nullptr;      // the bound matrix: target of assemble, operator of spmv / solve
   int64_t next_mat_id = 1;

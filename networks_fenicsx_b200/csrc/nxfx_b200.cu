@@ -9,6 +9,7 @@
 
 #include "assemble.cuh"
 #include "ctx.cuh"
+#include "condense.cuh"
 #include "generic.cuh"
 #include "precond.cuh"
 #include "spmv.cuh"
@@ -84,6 +85,22 @@ PeerDev make_peer(nxfx_ctx* c, int ch) {
   p.epoch = ++c->comm.epoch[ch];
   p.err = c->comm.err_d;
   return p;
+}
+
+CondDev make_cond(nxfx_ctx* ctx) {
+  auto& k = ctx->cond;
+  CondDev c;
+  c.n_max = k.n_max; c.kl = k.kl; c.kv = 2 * k.kl; c.ldab = 3 * k.kl + 1;
+  c.per_edge = k.per_edge; c.pcell_base = k.pcell_base; c.pcell_stride = k.pcell_stride; c.cont = k.cont;
+  c.type_n = k.type_n.p; c.loc_ptr = k.loc_ptr.p; c.loc_kind = k.loc_kind.p; c.loc_off = k.loc_off.p;
+  c.k_ptr = k.k_ptr.p; c.k_row = k.k_row.p; c.k_col = k.k_col.p; c.k_cell = k.k_cell.p; c.k_coef = k.k_coef.p;
+  c.c_ptr = k.c_ptr.p; c.c_row = k.c_row.p; c.c_slot = k.c_slot.p; c.c_coef = k.c_coef.p;
+  c.d_ptr = k.d_ptr.p; c.d_slot = k.d_slot.p; c.d_col = k.d_col.p; c.d_coef = k.d_coef.p;
+  c.bif_node = k.bif_node.p;
+  c.band = k.band.p; c.ipiv = k.ipiv.p; c.Y = k.Y.p; c.S = k.S.p; c.y0 = k.y0.p; c.h = k.h.p;
+  c.bd0 = k.bd0.p; c.bU = k.bU.p; c.bL = k.bL.p; c.bDinv = k.bDinv.p; c.bG = k.bG.p; c.bH = k.bH.p;
+  c.br = k.br.p; c.bz = k.bz.p;
+  return c;
 }
 
 int vec_grid(const nxfx_ctx* c, int64_t n) {
@@ -387,8 +404,49 @@ int tree_pass(nxfx_ctx* ctx, bool factor, const double* fuse_r = nullptr, bool f
   return NXFX_OK;
 }
 
+// ---- table-driven path: exact condensation (condense.cuh) ---------------------------------------
+constexpr int kCondThreads = 128;
+
+int do_cond_setup(nxfx_ctx* ctx) {
+  NXFX_REQUIRE(ctx, ctx->cond.set, "nxfx_set_condensation has not been called");
+  NXFX_REQUIRE(ctx, ctx->tree.set, "nxfx_set_tree_schedule has not been called");
+  Net g = make_net(ctx);
+  CondDev c = make_cond(ctx);
+  NXFX_LAUNCH(ctx, cond_factor_kernel, (int)cdiv(ctx->E, kCondThreads), kCondThreads, 0, g, c, ctx->cur->cell_rh.p);
+  if (ctx->n_bif > 0) {
+    TreeDev t = make_tree(ctx);
+    NXFX_LAUNCH(ctx, cond_node_kernel<true>, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, c, nullptr);
+    const int nb = ctx->tree.n_chunks - 1;
+    if (nb > 0) NXFX_LAUNCH(ctx, btree_sweep_kernel<0>, nb, 1024, 0, t, c, 0);
+    NXFX_LAUNCH(ctx, btree_sweep_kernel<0>, 1, 1024, 0, t, c, nb);
+  }
+  ctx->pc_ready = true;
+  ctx->pc_mat = ctx->cur->id;
+  return NXFX_OK;
+}
+
+int do_cond_apply(nxfx_ctx* ctx, const double* r, double* z, bool add) {
+  NXFX_REQUIRE(ctx, ctx->pc_ready, "pc_setup has not been run");
+  Net g = make_net(ctx);
+  CondDev c = make_cond(ctx);
+  TreeDev t = make_tree(ctx);
+  NXFX_LAUNCH(ctx, cond_edge_rhs_kernel, (int)cdiv(ctx->E, kCondThreads), kCondThreads, 0, g, c, r);
+  if (ctx->n_bif > 0) {
+    NXFX_LAUNCH(ctx, cond_node_kernel<false>, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, c, r);
+    const int nb = ctx->tree.n_chunks - 1;
+    if (nb > 0) NXFX_LAUNCH(ctx, btree_sweep_kernel<1>, nb, 1024, 0, t, c, 0);
+    NXFX_LAUNCH(ctx, btree_sweep_kernel<3>, 1, 1024, 0, t, c, nb);
+    if (nb > 0) NXFX_LAUNCH(ctx, btree_sweep_kernel<2>, nb, 1024, 0, t, c, 0);
+  }
+  const int grid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kCondThreads);
+  if (add) NXFX_LAUNCH(ctx, cond_backsub_kernel<true>, grid, kCondThreads, 0, g, t, c, z);
+  else NXFX_LAUNCH(ctx, cond_backsub_kernel<false>, grid, kCondThreads, 0, g, t, c, z);
+  return NXFX_OK;
+}
+
 int do_pc_setup(nxfx_ctx* ctx) {
   NXFX_REQUIRE(ctx, is_assembled(ctx), "assemble the matrix before pc_setup");
+  if (ctx->generic) return do_cond_setup(ctx);
   NXFX_REQUIRE(ctx, ctx->tree.set, "nxfx_set_tree_schedule has not been called");
   const bool n1 = ctx->N == 1 && ctx->tree.fast_ok;  // (the global-memory fallback sweeps read edge_g)
   if (!n1)
@@ -409,7 +467,7 @@ int do_pc_setup(nxfx_ctx* ctx) {
 
 // factorisation and first application z = P^{-1} r in one cooperative launch
 bool can_fuse_setup(const nxfx_ctx* ctx) {
-  return ctx->tree.set && ctx->tree.fast_ok && ctx->tree.coop_fs_ok && ctx->n_bif > 0 &&
+  return !ctx->generic && ctx->tree.set && ctx->tree.fast_ok && ctx->tree.coop_fs_ok && ctx->n_bif > 0 &&
          ctx->tree.n_chunks > 1 && (!ctx->lam_weight.p || ctx->comm.ready) && ctx->cur->acc_count == 1;
 }
 
@@ -537,6 +595,7 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
     return NXFX_OK;
   }
   NXFX_REQUIRE(ctx, ctx->pc_ready, "pc_setup has not been run");
+  if (ctx->generic) return do_cond_apply(ctx, r, z, add);
   Net g = make_net(ctx);
   TreeDev t = make_tree(ctx);
   const int bgrid = (int)cdiv((int64_t)ctx->E + ctx->n_bif, kThreads);
@@ -1274,8 +1333,8 @@ int nxfx_solve(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_opts*
   NXFX_REQUIRE(ctx, is_assembled(ctx), "matrix has not been assembled");
   std::memset(info, 0, sizeof *info);
   int rc;
-  if (opts->pc_type == NXFX_PC_NETWORK_SCHUR && ctx->generic)
-    return fail(ctx, NXFX_ERR_UNSUPPORTED, "the network Schur preconditioner is implemented for flux P1 / pressure DG0");
+  if (opts->pc_type == NXFX_PC_NETWORK_SCHUR && ctx->generic && !ctx->cond.set)
+    return fail(ctx, NXFX_ERR_UNSUPPORTED, "higher-order elements: call nxfx_set_condensation before a direct solve");
   bool fused_setup = false;
   if (ctx->comm.ready)
     NXFX_REQUIRE(ctx, can_fuse_setup(ctx) || (ctx->pc_ready && ctx->cur->acc_count == 1),
@@ -1364,6 +1423,7 @@ int nxfx_set_generic_system(nxfx_ctx* ctx, int32_t n_dofs, int32_t n_flux_rows, 
   }
   int rc;
   ctx->has_pattern = ctx->pc_ready = false;
+  ctx->cond.set = false;
   release_matrices(ctx);
   ctx->ndofs = n_dofs; ctx->nq = n_flux_rows; ctx->nnz = nnz;
   ctx->poff = n_flux_rows; ctx->loff = n_dofs - ctx->n_bif;
@@ -1403,6 +1463,13 @@ int nxfx_assemble_generic(nxfx_ctx* ctx, const double* R_cell, double R_const, c
     else
       NXFX_LAUNCH(ctx, assemble_generic_kernel<false>, vec_grid(ctx, ctx->nnz), kThreads, 0, ctx->nnz, sid, sco,
                   ctx->gen_cell_h.p, R_cell, R_const, ctx->cur->vals.p);
+    // R*h per cell travels with the values (the condensation is built from it), accumulated like them
+    if (accumulate && ctx->cur->assembled)
+      NXFX_LAUNCH(ctx, cell_rh_generic_kernel<true>, vec_grid(ctx, ctx->nc), kThreads, 0, ctx->nc, ctx->gen_cell_h.p, R_cell,
+                  R_const, ctx->cur->cell_rh.p);
+    else
+      NXFX_LAUNCH(ctx, cell_rh_generic_kernel<false>, vec_grid(ctx, ctx->nc), kThreads, 0, ctx->nc, ctx->gen_cell_h.p, R_cell,
+                  R_const, ctx->cur->cell_rh.p);
     note_lhs_assembled(ctx, accumulate);
   }
   if (rhs) {
@@ -1414,6 +1481,84 @@ int nxfx_assemble_generic(nxfx_ctx* ctx, const double* R_cell, double R_const, c
       NXFX_LAUNCH(ctx, rhs_generic_kernel<false>, (int)cdiv(n, kThreads), kThreads, 0, n, ctx->gen_bptr.p, ctx->gen_bid.p,
                   ctx->gen_bcoef.p, ctx->gen_cell_h.p, f_cell, f_const, g.x2, b);
   }
+  return NXFX_OK;
+}
+
+int nxfx_set_condensation(nxfx_ctx* ctx, int32_t continuous_pressure, int32_t flux_dofs_per_edge, int32_t n_max,
+                          int32_t kl, int32_t pcell_base, int32_t pcell_stride, const int32_t* type_n,
+                          const int32_t* loc_ptr, const int32_t* loc_kind, const int32_t* loc_off,
+                          const int32_t* k_ptr, const int32_t* k_row, const int32_t* k_col, const int32_t* k_cell,
+                          const double* k_coef, const int32_t* c_ptr, const int32_t* c_row, const int32_t* c_slot,
+                          const double* c_coef, const int32_t* d_ptr, const int32_t* d_slot, const int32_t* d_col,
+                          const double* d_coef, const int32_t* bif_node) {
+  if (!ctx) return NXFX_ERR_INVALID;
+  NXFX_REQUIRE(ctx, ctx->has_pattern && ctx->generic, "nxfx_set_generic_system has not been called");
+  NXFX_REQUIRE(ctx, type_n && loc_ptr && loc_kind && loc_off && k_ptr && k_row && k_col && k_cell && k_coef && c_ptr &&
+                        d_ptr && (ctx->n_bif == 0 || bif_node), "null input");
+  NXFX_REQUIRE(ctx, n_max > 0 && kl > 0 && flux_dofs_per_edge > 0 && pcell_base >= 0 && pcell_stride >= 0, "bad sizes");
+  auto& k = ctx->cond;
+  k.set = false;
+  ctx->pc_ready = false;
+  const int64_t E = ctx->E, nd = ctx->ndofs;
+  for (int t = 0; t < 4; ++t) {
+    const int n = type_n[t];
+    if (n <= 0 || n > n_max || loc_ptr[t + 1] - loc_ptr[t] != n) return fail(ctx, NXFX_ERR_INVALID, "condensation: bad type_n[%d]", t);
+    for (int i = loc_ptr[t]; i < loc_ptr[t + 1]; ++i) {
+      // the largest global index any edge can produce for this local unknown must be a dof
+      int64_t top;
+      switch (loc_kind[i]) {
+        case 0: top = (E - 1) * flux_dofs_per_edge + loc_off[i]; break;
+        case 1: top = pcell_base + (E - 1) * (int64_t)pcell_stride + loc_off[i]; break;
+        case 2: top = ctx->nq + ctx->n_nodes + (E - 1) * (int64_t)(ctx->N - 1) + loc_off[i]; break;
+        case 3: case 4: top = ctx->nq + ctx->n_nodes - 1; break;
+        default: return fail(ctx, NXFX_ERR_INVALID, "condensation: unknown kind %d", loc_kind[i]);
+      }
+      if (loc_off[i] < 0 || top >= nd) return fail(ctx, NXFX_ERR_INVALID, "condensation: local unknown %d out of range", i);
+    }
+    for (int i = k_ptr[t]; i < k_ptr[t + 1]; ++i)
+      if (k_row[i] < 0 || k_row[i] >= n || k_col[i] < 0 || k_col[i] >= n || std::abs(k_row[i] - k_col[i]) > kl ||
+          k_cell[i] >= ctx->N)
+        return fail(ctx, NXFX_ERR_INVALID, "condensation: K entry %d out of range", i);
+    for (int i = c_ptr[t]; i < c_ptr[t + 1]; ++i)
+      if (c_row[i] < 0 || c_row[i] >= n || c_slot[i] < 0 || c_slot[i] > 3) return fail(ctx, NXFX_ERR_INVALID, "condensation: C entry %d out of range", i);
+    for (int i = d_ptr[t]; i < d_ptr[t + 1]; ++i)
+      if (d_col[i] < 0 || d_col[i] >= n || d_slot[i] < 0 || d_slot[i] > 3) return fail(ctx, NXFX_ERR_INVALID, "condensation: D entry %d out of range", i);
+  }
+  for (int32_t b = 0; b < ctx->n_bif; ++b)
+    if (bif_node[b] < 0 || bif_node[b] >= ctx->n_nodes) return fail(ctx, NXFX_ERR_INVALID, "condensation: bif_node[%d] out of range", b);
+  int rc;
+  if ((rc = upload(ctx, k.type_n, type_n, 4))) return rc;
+  if ((rc = upload(ctx, k.loc_ptr, loc_ptr, 5))) return rc;
+  if ((rc = upload(ctx, k.loc_kind, loc_kind, (size_t)loc_ptr[4]))) return rc;
+  if ((rc = upload(ctx, k.loc_off, loc_off, (size_t)loc_ptr[4]))) return rc;
+  if ((rc = upload(ctx, k.k_ptr, k_ptr, 5))) return rc;
+  if ((rc = upload(ctx, k.k_row, k_row, (size_t)k_ptr[4]))) return rc;
+  if ((rc = upload(ctx, k.k_col, k_col, (size_t)k_ptr[4]))) return rc;
+  if ((rc = upload(ctx, k.k_cell, k_cell, (size_t)k_ptr[4]))) return rc;
+  if ((rc = upload(ctx, k.k_coef, k_coef, (size_t)k_ptr[4]))) return rc;
+  if ((rc = upload(ctx, k.c_ptr, c_ptr, 5))) return rc;
+  if ((rc = upload(ctx, k.c_row, c_row, (size_t)c_ptr[4]))) return rc;
+  if ((rc = upload(ctx, k.c_slot, c_slot, (size_t)c_ptr[4]))) return rc;
+  if ((rc = upload(ctx, k.c_coef, c_coef, (size_t)c_ptr[4]))) return rc;
+  if ((rc = upload(ctx, k.d_ptr, d_ptr, 5))) return rc;
+  if ((rc = upload(ctx, k.d_slot, d_slot, (size_t)d_ptr[4]))) return rc;
+  if ((rc = upload(ctx, k.d_col, d_col, (size_t)d_ptr[4]))) return rc;
+  if ((rc = upload(ctx, k.d_coef, d_coef, (size_t)d_ptr[4]))) return rc;
+  if ((rc = upload(ctx, k.bif_node, bif_node, (size_t)ctx->n_bif))) return rc;
+  NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  k.n_max = n_max; k.kl = kl; k.per_edge = flux_dofs_per_edge; k.pcell_base = pcell_base; k.pcell_stride = pcell_stride;
+  k.cont = continuous_pressure ? 1 : 0;
+  const size_t Es = (size_t)E, nb = (size_t)std::max(ctx->n_bif, 1);
+  NXFX_CUDA(ctx, k.band.alloc((size_t)(3 * kl + 1) * n_max * Es));
+  NXFX_CUDA(ctx, k.ipiv.alloc((size_t)n_max * Es));
+  NXFX_CUDA(ctx, k.Y.alloc((size_t)4 * n_max * Es));
+  NXFX_CUDA(ctx, k.S.alloc(16 * Es));
+  NXFX_CUDA(ctx, k.y0.alloc((size_t)n_max * Es));
+  NXFX_CUDA(ctx, k.h.alloc(4 * Es));
+  for (auto* buf : {&k.bd0, &k.bU, &k.bL, &k.bDinv, &k.bG, &k.bH}) NXFX_CUDA(ctx, buf->alloc(4 * nb));
+  NXFX_CUDA(ctx, k.br.alloc(2 * nb));
+  NXFX_CUDA(ctx, k.bz.alloc(2 * nb));
+  k.set = true;
   return NXFX_OK;
 }
 

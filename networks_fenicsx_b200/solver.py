@@ -1,7 +1,7 @@
 """Solver interface for network problems (drop-in for ``networks_fenicsx.solver.Solver``,
 solver.py:16-143).  PETSc KSP / MUMPS are replaced by the device solver behind ``nxfx_solve``:
-the network Schur-complement preconditioner (exact on tree networks) used either as a direct
-solver with iterative refinement (``ksp_type=preonly``, the reference's default with
+the network Schur-complement preconditioner (exact on tree networks, for every polynomial degree)
+used either as a direct solver with iterative refinement (``ksp_type=preonly``, the reference's default with
 ``pc_type=lu``) or inside flexible GMRES."""
 
 from __future__ import annotations
@@ -157,26 +157,8 @@ class Solver:
         ksp_type = str(o.get("ksp_type", "preonly")).lower()
         pc_type = str(o.get("pc_type", "lu")).lower()
         opts = _lib.SolveOpts()
-        if self.assembler.is_generic and pc_type in _DIRECT_PCS:
-            # higher-order elements: the network Schur condensation is implemented for P1/DG0;
-            # direct-solver accuracy is obtained with (long-restart) GMRES instead
-            if not getattr(self, "_warned_generic_direct", False):
-                import warnings  # noqa: PLC0415
-
-                warnings.warn(
-                    f"pc_type={pc_type!r} (a direct solve) with flux/pressure degrees {self.assembler.degrees}: the exact "
-                    "network condensation exists for degrees (1, 0); this system is solved with restarted GMRES + "
-                    "flux-Jacobi to ksp_rtol (default 1e-12) and raises if that is not reached", stacklevel=3)
-                self._warned_generic_direct = True
-            opts.pc_type = _lib.PC_JACOBI_FLUX
-            opts.ksp_type = _lib.KSP_FGMRES
-            opts.rtol = float(o.get("ksp_rtol", 1e-12))
-            opts.atol = float(o.get("ksp_atol", 1e-50))
-            opts.max_it = int(o.get("ksp_max_it", 20000))
-            opts.restart = int(o.get("ksp_gmres_restart", min(self.assembler.num_dofs, 200)))
-            # a direct solver never hands back an unconverged iterate silently
-            opts.error_if_not_converged = int(bool(o.get("ksp_error_if_not_converged", True)))
-            return opts
+        # (higher-order elements take the same route: their exact condensation -- per-edge banded LU + 2 x 2 node
+        # blocks over the same schedule, condense.py / condense.cuh -- sits behind PC_NETWORK_SCHUR too)
         if pc_type in _DIRECT_PCS:
             opts.pc_type = _lib.PC_NETWORK_SCHUR
         elif pc_type == "none":
