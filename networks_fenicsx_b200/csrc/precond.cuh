@@ -159,6 +159,14 @@ __device__ __forceinline__ double n1_node_diag(const FusedN1& f, const TreeDev& 
   return d;
 }
 
+// (Measured and rejected, round 2: a prefetch.global.L2 pass over all of a chunk's gather addresses before the
+// evaluation -- the staging is bound by DRAM throughput on scattered 32-byte sectors, not by the latency of the
+// dependent loads -- and ordering a node's incidences by graph edge instead of by flux slot: r_p gathers get
+// contiguous, R h / r_q gathers lose what they gain; 48.5 vs 50.6 sectors per warp and incidence.)
+#ifndef NXFX_TREE_PAIR
+#define NXFX_TREE_PAIR 1
+#endif
+
 // schedule-ordered incidence table (built once per schedule)
 __global__ void __launch_bounds__(kThreads)
 t_inc_len_kernel(int n_bif, const int32_t* __restrict__ bif_of_t, const int32_t* __restrict__ bif_ptr,
@@ -175,7 +183,8 @@ t_inc_fill_kernel(int n_bif, const int32_t* __restrict__ bif_of_t, const int32_t
   if (n >= n_bif) return;
   const int bi = bif_of_t[n];
   int o = t_inc_ptr[n];
-  for (int k = bif_ptr[bi]; k < bif_ptr[bi + 1]; ++k, ++o) {
+  const int k0 = bif_ptr[bi], deg = bif_ptr[bi + 1] - k0;
+  for (int k = k0; k < k0 + deg; ++k, ++o) {
     const int inc = bif_inc[k], e = inc >> 1;
     t_inc[o] = make_int2(2 * edge_slot[e] | (inc & 1), e);
   }
@@ -836,7 +845,21 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
     sweep_up(S, ci, [&](int n) {
       const int i = n - b0;
       double ad = S.b[i], ar = S.a[i];
-      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+      int k = S.cptr[i];
+      const int k1 = S.cptr[i + 1];
+#if NXFX_TREE_PAIR
+      // binary nodes: the loads of both children are issued together (the level's cost is its dependent chain);
+      // the sums run in the same order as the loop below
+      for (; k + 2 <= k1; k += 2) {
+        const int c0 = S.cidx[k] - b0, c1 = S.cidx[k + 1] - b0;
+        const int j0 = max(c0, 0), j1 = max(c1, 0);
+        const double e0 = Se[j0], g0 = S.c[j0], a0 = S.a[j0];
+        const double e1 = Se[j1], g1 = S.c[j1], a1 = S.a[j1];
+        if (c0 >= 0) { ad -= e0 * g0; ar += g0 * a0; }
+        if (c1 >= 0) { ad -= e1 * g1; ar += g1 * a1; }
+      }
+#endif
+      for (; k < k1; ++k) {
         const int c = S.cidx[k] - b0;
         if (c >= 0) {
           ad -= Se[c] * S.c[c];
@@ -960,8 +983,8 @@ tree_factor_solve_coop_kernel(TreeDev t, int n_bottom, unsigned int* ticket, uns
   int chunk = (int)blockIdx.x;
   ChunkInfo cm = ci;
   while (true) {
-    factor_solve_up(t, S, Se, cm, false, fin);
     const bool more = chunk + G < n_bottom;
+    factor_solve_up(t, S, Se, cm, false, fin);
     // the chunk roots for the top chunk -- and every node of a chunk that has to leave shared memory
     for (int i = threadIdx.x; i < cm.b1 - cm.b0; i += blockDim.x)
       if (more || S.par[i] < cm.b0 || S.par[i] >= cm.b1) t.r[cm.b0 + i] = S.a[i];
