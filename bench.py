@@ -200,6 +200,19 @@ class Problem:
         return ms / steps, launches
 
 
+def colouring_note(E, world):
+    """Which colouring the flux-block layout of this run comes from (mesh.color_graph)."""
+    from networks_fenicsx_b200 import mesh as _mesh
+
+    scope = "" if world == 1 else " of this rank's sub-network"
+    if E <= _mesh.NETWORKX_COLORING_MAX_EDGES:
+        return f"networkx greedy_color(line_graph, smallest_last){scope}: the reference's own call"
+    if E <= _mesh.NETWORKX_IDENTICAL_MAX_EDGES:
+        return (f"networkx-identical smallest_last{scope}, reproduced edge by edge without networkx graphs "
+                "(pinned by networkx fixtures at 16 and 20 generations)")
+    return f"native greedy in input order{scope} (beyond the size the networkx assignment is reproduced for; warned)"
+
+
 def per_cell(coef, E, N, default):
     """Scalar / per-graph-edge / per-cell coefficient -> [E, N]."""
     if coef is None:
@@ -544,7 +557,7 @@ def run_gpu(args):
                              "partial sums into every rank's buffer over NVLink (CUDA IPC), flag, wait, sum in rank order; no NCCL "
                              "call and one host sync per solve" if pb.exchange == "peer" else
                              "2 torch.distributed/NCCL all-reduces per solve between split kernel phases")) if world > 1 else "single GPU",
-            "colouring": "native greedy (input order); permutation-equivalent to networkx smallest_last, not identical -- see DESIGN.md",
+            "colouring": colouring_note(E, world),
             "l2": "per-step working set ~0.6 GB > 126 MB L2, no flush",
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (int(8 * nv) + int(coef_bytes)) * world,
@@ -587,6 +600,9 @@ def run_gpu(args):
                           "value": ps.n_dofs_total / (ms_s * 1e-3), "unit": UNIT, "gpu_launches_per_step": launches_s / max(5, args.steps // 2),
                           "exchange": ps.exchange, "parity": {k: par_s[k] for k in ("true_residual_recomputed", "kirchhoff_max", "rel_l2_vs_closed_form")},
                           "note": "fixed problem size at every N: speed-up(N) = ms_per_step(1) / ms_per_step(N)"}
+    # ---- higher-order elements (north_star item 1: P(k+1) flux / P(k) pressure): a side measurement ------------
+    if world == 1 and args.higher_order_generations > 0 and args.workload == "tree":
+        line["higher_order"] = higher_order_block(args.higher_order_generations, local_rank, max(3, args.steps // 4))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload, n, N, steps=1, warmup=0)
     if rank == 0:
@@ -594,6 +610,42 @@ def run_gpu(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def higher_order_block(n, device_index, steps):
+    """P2/P1 and P3/P2 on make_tree(n), 4 cells per edge: table-driven assembly + the exact condensation (per-edge
+    banded LU, 2 x 2 node blocks over the tree schedule) as ``preonly + lu`` -- one application and the residual
+    check per step.  The residual is the solver's own true residual ||b - A x|| / ||b|| on the assembled CSR."""
+    import ctypes as C
+
+    import networks_fenicsx_b200 as nxfx
+    from networks_fenicsx_b200 import _lib
+
+    out = {"workload": f"make_tree(n={n},H={n},W={n}), N=4, smallest_last, direct solve (preonly + lu)"}
+    for fd, pd in ((2, 1), (3, 2)):
+        G = nxfx.network_generation.make_tree(n, float(n), float(n), as_arrays=True)
+        nm = nxfx.NetworkMesh(G, N=4, color_strategy="smallest_last", device=device_index)
+        asm = nxfx.HydraulicNetworkAssembler(nm, flux_degree=fd, pressure_degree=pd)
+        asm.compute_forms(p_bc_ex=p_bc)
+        solver = nxfx.Solver(asm)
+        dev = nm.device
+        opts, info = solver.solve_options(), _lib.SolveInfo()
+
+        def step():
+            solver.assemble()
+            dev.call("nxfx_solve", solver.b.device_ptr(), solver.x.device_ptr_overwrite(), C.byref(opts), C.byref(info))
+
+        step()
+        l0 = dev.launch_count
+        dev.timer_start()
+        for _ in range(steps):
+            step()
+        ms = dev.timer_stop() / steps
+        out[f"P{fd}/P{pd}"] = {"n_dofs": asm.num_dofs, "nnz": solver.A.nnz, "ms_per_step": ms, "value": asm.num_dofs / (ms * 1e-3),
+                               "unit": UNIT, "relative_residual": info.residual_norm / info.rhs_norm,
+                               "iterations": int(info.iterations), "gpu_launches_per_step": (dev.launch_count - l0) / steps}
+        del solver, asm, nm
+    return out
 
 
 # ---- CPU baseline: the oracle port timed on the host ---------------------------------------------
@@ -682,6 +734,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = n + log2(N) generations (one ~20-generation subtree per GPU), strong = same tree")
+    ap.add_argument("--higher-order-generations", type=int, default=16,
+                    help="P2/P1 and P3/P2 side measurement on make_tree(m), N=4 (single GPU); 0 = skip")
     ap.add_argument("--strong-generations", type=int, default=23,
                     help="fixed tree of the extra strong-scaling block printed at every N (0 = off)")
     args = ap.parse_args()
