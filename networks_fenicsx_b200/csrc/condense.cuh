@@ -80,28 +80,74 @@ __device__ __forceinline__ int cond_glob(const Net& g, const CondDev& c, int e, 
   }
 }
 
-#define NXFX_AB(i, j) band[((size_t)(c.kv + (i) - (j)) * c.n_max + (j)) * E + e]
+// Views with a run-time stride: one thread's band / vector either in global memory (stride = number of edges:
+// a warp's accesses coalesce) or in shared memory (stride = threads per block: conflict-free).
+struct BandRef {
+  double* p;
+  size_t s;
+  int kv, n_max;
+  __device__ __forceinline__ double& operator()(int i, int j) const { return p[((size_t)(kv + i - j) * n_max + j) * s]; }
+};
+struct VecRef {
+  double* p;
+  size_t s;
+  __device__ __forceinline__ double& operator[](int k) const { return p[(size_t)k * s]; }
+};
 
-// dgbtrs (no transpose) on one vector b[k * E], in place
-__device__ __forceinline__ void cond_band_solve(const CondDev& c, size_t E, int e, int n, double* __restrict__ b) {
-  const double* __restrict__ band = c.band;
+// dgbtf2: unblocked banded LU with partial pivoting, kl sub- and kl super-diagonals, fill up to kv = 2 kl
+__device__ __forceinline__ void cond_band_lu(const BandRef& A, int n, int kl, int32_t* __restrict__ ipiv, size_t ips) {
+  int ju = 0;
   for (int j = 0; j < n; ++j) {
-    const int l = c.ipiv[(size_t)j * E + e];
-    double bj = b[(size_t)l * E];
-    if (l != j) { b[(size_t)l * E] = b[(size_t)j * E]; b[(size_t)j * E] = bj; }
-    const int lm = min(c.kl, n - 1 - j);
-    if (bj != 0.0)
-      for (int i = 1; i <= lm; ++i) b[(size_t)(j + i) * E] -= NXFX_AB(j + i, j) * bj;
-  }
-  for (int j = n - 1; j >= 0; --j) {
-    const double bj = b[(size_t)j * E] / NXFX_AB(j, j);
-    b[(size_t)j * E] = bj;
-    if (bj != 0.0)
-      for (int i = max(0, j - c.kv); i < j; ++i) b[(size_t)i * E] -= NXFX_AB(i, j) * bj;
+    const int km = min(kl, n - 1 - j);
+    int jp = 0;
+    double best = fabs(A(j, j));
+    for (int i = 1; i <= km; ++i) {
+      const double a = fabs(A(j + i, j));
+      if (a > best) { best = a; jp = i; }
+    }
+    ipiv[(size_t)j * ips] = j + jp;
+    ju = max(ju, min(j + jp + kl, n - 1));  // last column the pivot row reaches
+    if (jp != 0)
+      for (int col = j; col <= ju; ++col) {
+        const double t = A(j, col);
+        A(j, col) = A(j + jp, col);
+        A(j + jp, col) = t;
+      }
+    // (a zero pivot -- singular K_e -- propagates inf / nan: the residual check of the solve reports it)
+    const double inv = 1.0 / A(j, j);
+    for (int i = 1; i <= km; ++i) A(j + i, j) *= inv;
+    for (int col = j + 1; col <= ju; ++col) {
+      const double ujc = A(j, col);
+      if (ujc != 0.0)
+        for (int i = 1; i <= km; ++i) A(j + i, col) -= A(j + i, j) * ujc;
+    }
   }
 }
 
-// K_e from the entry lists, banded LU with partial pivoting (dgbtf2), Y_e = K_e^{-1} C_e, S_e = -D_e Y_e
+// dgbtrs (no transpose) on one vector, in place
+__device__ __forceinline__ void cond_band_solve(const BandRef& A, int n, int kl, const int32_t* __restrict__ ipiv,
+                                                size_t ips, const VecRef& b) {
+  for (int j = 0; j < n; ++j) {
+    const int l = ipiv[(size_t)j * ips];
+    const double bj = b[l];
+    if (l != j) { b[l] = b[j]; b[j] = bj; }
+    const int lm = min(kl, n - 1 - j);
+    if (bj != 0.0)
+      for (int i = 1; i <= lm; ++i) b[j + i] -= A(j + i, j) * bj;
+  }
+  for (int j = n - 1; j >= 0; --j) {
+    const double bj = b[j] / A(j, j);
+    b[j] = bj;
+    if (bj != 0.0)
+      for (int i = max(0, j - A.kv); i < j; ++i) b[i] -= A(i, j) * bj;
+  }
+}
+
+// K_e from the entry lists, banded LU with partial pivoting, Y_e = K_e^{-1} C_e, S_e = -D_e Y_e.
+// The band stays in global memory (edge-fastest: coalesced, L2-resident per block of edges).  Measured: staging
+// it in shared memory leaves room for 64-128 threads per SM only, and the LU -- a chain of dependent FP64
+// read-modify-writes -- then has nothing to hide its latency behind: 1.9 / 7.0 ms instead of 1.8 / 4.9 ms for
+// P2/P1 / P3/P2 at 524 k edges.
 __global__ void __launch_bounds__(128)
 cond_factor_kernel(Net g, CondDev c, const double* __restrict__ cell_rh) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,82 +155,60 @@ cond_factor_kernel(Net g, CondDev c, const double* __restrict__ cell_rh) {
   const size_t E = (size_t)g.E;
   const EdgeInfo ei = cond_edge(g, c, e);
   const int n = ei.n;
-  double* __restrict__ band = c.band;
+  const BandRef A{c.band + e, E, c.kv, c.n_max};
   for (int r = 0; r < c.ldab; ++r)
-    for (int j = 0; j < n; ++j) band[((size_t)r * c.n_max + j) * E + e] = 0.0;
+    for (int j = 0; j < n; ++j) A.p[((size_t)r * c.n_max + j) * A.s] = 0.0;
   for (int k = c.k_ptr[ei.type]; k < c.k_ptr[ei.type + 1]; ++k) {
     const int cell = c.k_cell[k];
-    const double v = cell >= 0 ? c.k_coef[k] * cell_rh[(size_t)e * g.N + cell] : c.k_coef[k];
-    NXFX_AB(c.k_row[k], c.k_col[k]) += v;
+    A(c.k_row[k], c.k_col[k]) += cell >= 0 ? c.k_coef[k] * cell_rh[(size_t)e * g.N + cell] : c.k_coef[k];
   }
-  int ju = 0;
-  for (int j = 0; j < n; ++j) {
-    const int km = min(c.kl, n - 1 - j);
-    int jp = 0;
-    double best = fabs(NXFX_AB(j, j));
-    for (int i = 1; i <= km; ++i) {
-      const double a = fabs(NXFX_AB(j + i, j));
-      if (a > best) { best = a; jp = i; }
-    }
-    c.ipiv[(size_t)j * E + e] = j + jp;
-    ju = max(ju, min(j + jp + c.kl, n - 1));  // last column the pivot row reaches
-    if (jp != 0)
-      for (int col = j; col <= ju; ++col) {
-        const double t = NXFX_AB(j, col);
-        NXFX_AB(j, col) = NXFX_AB(j + jp, col);
-        NXFX_AB(j + jp, col) = t;
-      }
-    const double piv = NXFX_AB(j, j);  // a zero pivot (singular K_e) propagates inf / nan: the residual check reports it
-    const double inv = 1.0 / piv;
-    for (int i = 1; i <= km; ++i) NXFX_AB(j + i, j) *= inv;
-    for (int col = j + 1; col <= ju; ++col) {
-      const double ujc = NXFX_AB(j, col);
-      if (ujc != 0.0)
-        for (int i = 1; i <= km; ++i) NXFX_AB(j + i, col) -= NXFX_AB(j + i, j) * ujc;
-    }
-  }
-  // Y = K^{-1} C for the active nodal slots
-  for (int s = 0; s < 4; ++s)
-    for (int k = 0; k < n; ++k) c.Y[((size_t)s * c.n_max + k) * E + e] = 0.0;
-  for (int k = c.c_ptr[ei.type]; k < c.c_ptr[ei.type + 1]; ++k)
-    c.Y[((size_t)c.c_slot[k] * c.n_max + c.c_row[k]) * E + e] += c.c_coef[k];
-  for (int s = 0; s < 4; ++s) {
-    const bool active = ((s < 2 ? ei.lu : ei.lv) >= 0) && ((s & 1) || c.cont);
-    if (active) cond_band_solve(c, E, e, n, c.Y + (size_t)s * c.n_max * E + e);
-  }
+  cond_band_lu(A, n, c.kl, c.ipiv + e, E);
+  // Y = K^{-1} C column by column for the active nodal slots, S = -D Y
   double S[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) S[k] = 0.0;
-  for (int k = c.d_ptr[ei.type]; k < c.d_ptr[ei.type + 1]; ++k) {
-    const int a = c.d_slot[k], col = c.d_col[k];
-    const double co = c.d_coef[k];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const double y = c.Y[((size_t)s * c.n_max + col) * E + e];
+  for (int s = 0; s < 4; ++s) {
+    const VecRef yv{c.Y + (size_t)s * c.n_max * E + e, E};  // column s of Y_e, solved in place
+    const bool active = ((s < 2 ? ei.lu : ei.lv) >= 0) && ((s & 1) || c.cont);
+    for (int k = 0; k < n; ++k) yv[k] = 0.0;
+    if (!active) continue;
+    for (int k = c.c_ptr[ei.type]; k < c.c_ptr[ei.type + 1]; ++k)
+      if (c.c_slot[k] == s) yv[c.c_row[k]] += c.c_coef[k];
+    cond_band_solve(A, n, c.kl, c.ipiv + e, E, yv);
+    for (int k = c.d_ptr[ei.type]; k < c.d_ptr[ei.type + 1]; ++k) {
+      const int a = c.d_slot[k];
+      const double t = c.d_coef[k] * yv[c.d_col[k]];
 #pragma unroll
       for (int aa = 0; aa < 4; ++aa)
-        if (aa == a) S[aa * 4 + s] -= co * y;
+        if (aa == a) S[aa * 4 + s] -= t;
     }
   }
 #pragma unroll
   for (int k = 0; k < 16; ++k) c.S[(size_t)k * E + e] = S[k];
 }
 
-// y0 = K_e^{-1} r_loc, h_e = D_e y0
+// y0 = K_e^{-1} r_loc, h_e = D_e y0 (SMEM: the right-hand side is solved in shared memory -- n_max doubles per
+// thread, full occupancy; 298 instead of 335 us for P2/P1 at 524 k edges)
+template <bool SMEM>
 __global__ void __launch_bounds__(128)
 cond_edge_rhs_kernel(Net g, CondDev c, const double* __restrict__ r) {
+  extern __shared__ __align__(16) double cond_sm[];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= g.E) return;
-  const size_t E = (size_t)g.E;
+  const size_t E = (size_t)g.E, T = blockDim.x;
   const EdgeInfo ei = cond_edge(g, c, e);
   const int l0 = c.loc_ptr[ei.type];
-  double* __restrict__ y = c.y0 + e;
-  for (int k = 0; k < ei.n; ++k) y[(size_t)k * E] = r[cond_glob(g, c, e, ei, c.loc_kind[l0 + k], c.loc_off[l0 + k])];
-  cond_band_solve(c, E, e, ei.n, y);
+  const BandRef G{c.band + e, E, c.kv, c.n_max};
+  const VecRef y{SMEM ? cond_sm + threadIdx.x : c.y0 + e, SMEM ? T : E};
+  for (int k = 0; k < ei.n; ++k) y[k] = r[cond_glob(g, c, e, ei, c.loc_kind[l0 + k], c.loc_off[l0 + k])];
+  cond_band_solve(G, ei.n, c.kl, c.ipiv + e, E, y);
+  if (SMEM)
+    for (int k = 0; k < ei.n; ++k) c.y0[(size_t)k * E + e] = y[k];
   double h[4] = {0.0, 0.0, 0.0, 0.0};
   for (int k = c.d_ptr[ei.type]; k < c.d_ptr[ei.type + 1]; ++k) {
     const int a = c.d_slot[k];
-    const double t = c.d_coef[k] * y[(size_t)c.d_col[k] * E];
+    const double t = c.d_coef[k] * y[c.d_col[k]];
 #pragma unroll
     for (int aa = 0; aa < 4; ++aa)
       if (aa == a) h[aa] += t;
@@ -352,7 +376,6 @@ cond_backsub_kernel(Net g, TreeDev t, CondDev c, double* __restrict__ z) {
   }
 }
 
-#undef NXFX_AB
 
 // R*h per cell of the table-driven assembly (natural cell order), accumulated with the values
 template <bool ACC>

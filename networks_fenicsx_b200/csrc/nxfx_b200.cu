@@ -406,6 +406,18 @@ int tree_pass(nxfx_ctx* ctx, bool factor, const double* fuse_r = nullptr, bool f
 
 // ---- table-driven path: exact condensation (condense.cuh) ---------------------------------------
 constexpr int kCondThreads = 128;
+constexpr size_t kCondSmemMax = 220 * 1024;
+
+// threads per block of the shared-memory variants (0: does not fit, use the global-memory variant)
+bool cond_smem_enabled() {  // NXFX_COND_SMEM=0: global-memory variants only (A/B measurements)
+  static const bool on = [] { const char* e = std::getenv("NXFX_COND_SMEM"); return !(e && e[0] == '0'); }();
+  return on;
+}
+int cond_rhs_threads(const nxfx_ctx* ctx) {
+  if (!cond_smem_enabled()) return 0;
+  const size_t t = std::min<size_t>(kCondThreads, kCondSmemMax / ((size_t)ctx->cond.n_max * sizeof(double))) & ~(size_t)31;
+  return (int)t;
+}
 
 int do_cond_setup(nxfx_ctx* ctx) {
   NXFX_REQUIRE(ctx, ctx->cond.set, "nxfx_set_condensation has not been called");
@@ -430,7 +442,12 @@ int do_cond_apply(nxfx_ctx* ctx, const double* r, double* z, bool add) {
   Net g = make_net(ctx);
   CondDev c = make_cond(ctx);
   TreeDev t = make_tree(ctx);
-  NXFX_LAUNCH(ctx, cond_edge_rhs_kernel, (int)cdiv(ctx->E, kCondThreads), kCondThreads, 0, g, c, r);
+  const int tr = cond_rhs_threads(ctx);
+  if (tr > 0) {
+    NXFX_LAUNCH(ctx, cond_edge_rhs_kernel<true>, (int)cdiv(ctx->E, tr), tr, (size_t)c.n_max * sizeof(double) * tr, g, c, r);
+  } else {
+    NXFX_LAUNCH(ctx, cond_edge_rhs_kernel<false>, (int)cdiv(ctx->E, kCondThreads), kCondThreads, 0, g, c, r);
+  }
   if (ctx->n_bif > 0) {
     NXFX_LAUNCH(ctx, cond_node_kernel<false>, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, c, r);
     const int nb = ctx->tree.n_chunks - 1;
@@ -1548,6 +1565,7 @@ int nxfx_set_condensation(nxfx_ctx* ctx, int32_t continuous_pressure, int32_t fl
   NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   k.n_max = n_max; k.kl = kl; k.per_edge = flux_dofs_per_edge; k.pcell_base = pcell_base; k.pcell_stride = pcell_stride;
   k.cont = continuous_pressure ? 1 : 0;
+  NXFX_CUDA(ctx, cudaFuncSetAttribute(cond_edge_rhs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCondSmemMax));
   const size_t Es = (size_t)E, nb = (size_t)std::max(ctx->n_bif, 1);
   NXFX_CUDA(ctx, k.band.alloc((size_t)(3 * kl + 1) * n_max * Es));
   NXFX_CUDA(ctx, k.ipiv.alloc((size_t)n_max * Es));

@@ -415,6 +415,22 @@ def test_higher_order_direct_solve_at_size(fd, pd, n):
     assert np.linalg.norm(r) <= 1e-12 * np.linalg.norm(solver.b.array_r)
 
 
+def test_higher_order_long_edges():
+    """40 cells per edge (the arterial demo's refinement): the per-edge band no longer fits the shared-memory
+    variant of the LU, the global-memory variant takes over; same direct solve."""
+    G = ng.make_arterial_tree(N=5, direction=np.array([0.1, 1.0, 0.0]))
+    N = 40
+    nc = N * G.number_of_edges()
+    rng = np.random.default_rng(40)
+    R, f = rng.uniform(0.5, 2.0, nc), rng.normal(size=nc)
+    for fd, pd in ((2, 1), (3, 2), (2, 0)):
+        nm, asm, solver, net, A, b = run_ho_case(G, N, nx.coloring.strategy_largest_first, fd, pd, P_Y, R=R, f=f)
+        sol = solver.solve()
+        x = np.concatenate([fn.x.array for fn in sol])
+        assert helpers.rel_l2(x, net.solve(A, b)) < 1e-9, (fd, pd)
+        assert solver.ksp.getIterationNumber() <= 2
+
+
 def test_higher_order_accumulated_and_rhs_only():
     """ADD_VALUES twice and an rhs-only reassembly after changing R on the table-driven path: R*h accumulates with
     the values, the condensation follows the matrix as it stands (same contract as the P1/DG0 path)."""
