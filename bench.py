@@ -560,7 +560,9 @@ def run_gpu(args):
             "colouring": colouring_note(E, world),
             "l2": "per-step working set ~0.6 GB > 126 MB L2, no flush",
         },
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (int(8 * nv) + int(coef_bytes)) * world,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (int(asm.pbc_h2d_bytes) + int(coef_bytes)) * world,
+                "h2d_note": "p_bc: the caller hands over one value per mesh vertex; the forms read the boundary vertices only "
+                            "(assembly.py:258-260), so only their contiguous id runs are copied",
                 "d2h_bytes_per_step": int(8 * n_dofs) * world,
                 "path": "assembler.compute_forms(p_bc array) + solver.assemble() + solver.solve(functions)"},
         "gpu_launches": int(launches),

@@ -184,7 +184,18 @@ class HydraulicNetworkAssembler:
         self._pbc_host = pbc
         if self._pbc_d is None or self._pbc_d.n != pbc.size:
             self._pbc_d = dev.empty(pbc.size)
-        self._pbc_d.upload(pbc, sync=False)
+            self._pbc_d.zero()
+        # the forms read p_bc at BOUNDARY vertices only (assembly.py:258-260): when those are a few contiguous
+        # runs of vertex ids (generated trees: the inlet and the last generation) only the runs travel over PCIe
+        runs = self._boundary_runs()
+        if runs is None:
+            self._pbc_d.upload(pbc, sync=False)
+            self.pbc_h2d_bytes = pbc.nbytes
+        else:
+            for a, b in runs:
+                dev.call("nxfx_memcpy_h2d", C.c_void_p(self._pbc_d.ptr + 8 * a), C.c_void_p(pbc.ctypes.data + 8 * a),
+                         C.c_size_t(8 * (b - a)))
+            self.pbc_h2d_bytes = int(sum(8 * (b - a) for a, b in runs))
         dev.call("nxfx_set_boundary_pressure", self._pbc_d.c_ptr)  # into the vertex records
         dev.sync()
         nm._pbc_owner = self  # the vertex records now hold THIS assembler's boundary data
@@ -193,6 +204,21 @@ class HydraulicNetworkAssembler:
         C_ = nm.num_edge_colors
         self._a = _BilinearBlocks(C_)
         self._L = _LinearBlocks(C_)
+
+    def _boundary_runs(self, max_runs: int = 8):
+        """``[(first, last + 1), ...]`` of the boundary vertex ids if they form at most ``max_runs`` contiguous
+        runs, else ``None`` (upload everything)."""
+        if not hasattr(self, "_pbc_runs"):
+            bv = np.sort(np.asarray(self._network_mesh.boundary_values, dtype=np.int64))
+            runs = None
+            if bv.size:
+                cut = np.flatnonzero(np.diff(bv) != 1)
+                if cut.size + 1 <= max_runs:
+                    starts = np.concatenate([[0], cut + 1])
+                    ends = np.concatenate([cut, [bv.size - 1]])
+                    runs = [(int(bv[a]), int(bv[b]) + 1) for a, b in zip(starts, ends)]
+            self._pbc_runs = runs
+        return self._pbc_runs
 
     def _coefficient(self, val, default, nc, name, previous=None):
         """``previous``: the device array of the last call -- reused (no allocation, asynchronous upload)

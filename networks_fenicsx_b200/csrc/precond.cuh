@@ -826,7 +826,19 @@ __device__ __forceinline__ void factor_solve_up(const TreeDev& t, const TreeSmem
     return [&, shared_children_only](int n) {
       const int i = n - b0;
       double ad = S.b[i], ar = S.a[i];
-      for (int k = S.cptr[i]; k < S.cptr[i + 1]; ++k) {
+      int k = S.cptr[i];
+      const int k1 = S.cptr[i + 1];
+#if NXFX_TREE_PAIR
+      for (; k + 2 <= k1; k += 2) {  // both children in flight together (see the plain sweep below)
+        const int c0 = S.cidx[k] - b0, c1 = S.cidx[k + 1] - b0;
+        const int j0 = max(c0, 0), j1 = max(c1, 0);
+        const double e0 = Se[j0], g0 = S.c[j0], a0 = S.a[j0];
+        const double e1 = Se[j1], g1 = S.c[j1], a1 = S.a[j1];
+        if (c0 >= 0 && (!shared_children_only || tree_shared(S, c0))) { ad -= e0 * g0; ar += g0 * a0; }
+        if (c1 >= 0 && (!shared_children_only || tree_shared(S, c1))) { ad -= e1 * g1; ar += g1 * a1; }
+      }
+#endif
+      for (; k < k1; ++k) {
         const int c = S.cidx[k] - b0;
         if (c >= 0 && (!shared_children_only || tree_shared(S, c))) {
           ad -= Se[c] * S.c[c];

@@ -19,7 +19,7 @@ import numpy.typing as npt
 
 from .common import timed
 
-__all__ = ["make_tree", "make_arterial_tree", "ArrayGraph"]
+__all__ = ["make_tree", "make_arterial_tree", "tree_edges", "ArrayGraph"]
 
 
 @dataclasses.dataclass
@@ -77,6 +77,19 @@ def _tree_arrays(n: int, H: float, W: float, dim: int):
     parent = child // 2
     edges = np.stack([parent, child], axis=1)
     return pos, edges
+
+
+def tree_edges(n: int, r: int):
+    """Edges of the rooted tree at 0 with ``n`` nodes and branching ratio ``r`` in the order the reference's
+    generator yields them (network_generation.py:18-38): the root branch ``(0, 1)``, then every node ``k >= 2``
+    hangs below ``1 + (k - 2) // r`` -- closed form instead of the parent stack."""
+    if n == 0:
+        return
+    yield 0, 1
+    if n > 2 and r > 0:
+        k = np.arange(2, n)
+        for s, t in zip((1 + (k - 2) // r).tolist(), k.tolist()):
+            yield s, t
 
 
 @timed("nxfx:make_tree")

@@ -24,6 +24,29 @@ def graph_arrays(G):
 
 
 # ---- generators: bit-for-bit against the reference's make_tree / make_arterial_tree --------------
+def test_tree_edges_matches_reference_generator():
+    """network_generation.py:18-38 restated literally (parent stack) against the closed form."""
+    def literal(n, r):
+        if n == 0:
+            return
+        yield 0, 1
+        nodes = iter(range(1, n))
+        parents = [next(nodes)]
+        while parents:
+            source = parents.pop(0)
+            for _ in range(r):
+                try:
+                    target = next(nodes)
+                    parents.append(target)
+                    yield source, target
+                except StopIteration:
+                    break
+
+    for n in (0, 2, 3, 7, 8, 30, 100):  # (n = 1 raises inside the reference generator)
+        for r in (1, 2, 3, 5):
+            assert list(ng.tree_edges(n, r)) == list(literal(n, r)), (n, r)
+
+
 def test_make_tree_matches_reference_fixtures():
     keys = sorted({k.split("/")[0] for k in GOLDEN.files if k.startswith("tree_")})
     assert len(keys) >= 30
