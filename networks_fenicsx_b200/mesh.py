@@ -104,7 +104,20 @@ def _greedy_edge_coloring_arrays(n_nodes: int, edges: np.ndarray) -> np.ndarray:
         # process in rounds of mutually non-adjacent edges: an edge is ready when it is the
         # lowest-index uncoloured edge at both of its endpoints
         remaining = np.arange(E)
+        rounds = 0
         while remaining.size:
+            rounds += 1
+            if rounds > 64 and remaining.size > 1024:
+                # long chains (path-like graphs): a round colours a handful of edges only -- O(E) rounds of O(E)
+                # work.  Finish sequentially; same visiting order, same result.
+                used_l = used.tolist()
+                for e, u, v in zip(remaining.tolist(), u_all[remaining].tolist(), v_all[remaining].tolist()):
+                    free = ~(used_l[u] | used_l[v])
+                    low = free & -free
+                    colors[e] = low.bit_length() - 1
+                    used_l[u] |= low
+                    used_l[v] |= low
+                return colors
             first_at = np.full(n_nodes, E, dtype=np.int64)
             np.minimum.at(first_at, u_all[remaining], remaining)
             np.minimum.at(first_at, v_all[remaining], remaining)

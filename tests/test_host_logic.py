@@ -24,6 +24,32 @@ def graph_arrays(G):
 
 
 # ---- generators: bit-for-bit against the reference's make_tree / make_arterial_tree --------------
+def test_native_greedy_colouring_on_long_chains():
+    """Path-like graphs colour an edge or two per round: after 64 rounds the native greedy colouring finishes
+    sequentially (round-1 advice) -- same visiting order, same colours as the plain edge-by-edge loop."""
+    from networks_fenicsx_b200 import mesh as nxmesh
+
+    def plain(n_nodes, edges):
+        used = [set() for _ in range(n_nodes)]
+        out = []
+        for u, v in edges.tolist():
+            c = 0
+            while c in used[u] or c in used[v]:
+                c += 1
+            out.append(c)
+            used[u].add(c)
+            used[v].add(c)
+        return np.asarray(out)
+
+    E = 5000
+    path = np.stack([np.arange(E), np.arange(1, E + 1)], axis=1)
+    rng = np.random.default_rng(1)
+    chains = np.stack([np.maximum(np.arange(1, E + 1) - rng.integers(1, 3, E), 0), np.arange(1, E + 1)], axis=1)
+    for edges in (path, chains):
+        col = nxmesh._greedy_edge_coloring_arrays(E + 1, edges)
+        assert np.array_equal(col, plain(E + 1, edges))
+
+
 def test_tree_edges_matches_reference_generator():
     """network_generation.py:18-38 restated literally (parent stack) against the closed form."""
     def literal(n, r):
