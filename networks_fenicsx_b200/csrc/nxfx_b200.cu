@@ -505,12 +505,10 @@ int do_pc_setup_apply(nxfx_ctx* ctx, const double* r, double* z, bool add = fals
   if (!n1) {
     // several cells per edge: the per-edge condensation and the bifurcation sums are separate streaming
     // kernels; the tree kernel then stages the node arrays (diag0, tg, r) instead of the incidence table
-    NXFX_LAUNCH(ctx, edge_conductance_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, ctx->E, ctx->N,
-                ctx->cur->cell_rh.p, ctx->edge_g.p);
-    NXFX_LAUNCH(ctx, bif_diag_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, ctx->edge_g.p);
-    NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cur->cell_rh.p, r,
-                ctx->edge_c.p, ctx->edge_fn.p);
-    NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->edge_g.p,
+    // (two passes -- per edge, per bifurcation -- produce what the separate setup / apply kernels produce in four)
+    NXFX_LAUNCH(ctx, edge_condense_kernel<true>, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cur->cell_rh.p, r,
+                ctx->edge_c.p, ctx->edge_fn.p, ctx->edge_g.p);
+    NXFX_LAUNCH(ctx, bif_rhs_kernel<true>, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->edge_g.p,
                 ctx->edge_c.p, ctx->edge_fn.p, ctx->lam_weight.p);
     fin.r = nullptr;
     fin.cell_rh = nullptr;
@@ -633,10 +631,10 @@ int do_pc_apply(nxfx_ctx* ctx, int pc_type, const double* r, double* z, bool add
     else NXFX_LAUNCH(ctx, edge_backsub_n1_kernel<false>, bgrid, kThreads, 0, g, t, ctx->cur->cell_rh.p, r, z);
     return NXFX_OK;
   }
-  NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cur->cell_rh.p,
-              r, ctx->edge_c.p, ctx->edge_fn.p);
+  NXFX_LAUNCH(ctx, edge_condense_kernel<false>, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cur->cell_rh.p,
+              r, ctx->edge_c.p, ctx->edge_fn.p, nullptr);
   if (ctx->n_bif > 0) {
-    NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r,
+    NXFX_LAUNCH(ctx, bif_rhs_kernel<false>, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r,
                 ctx->edge_g.p, ctx->edge_c.p, ctx->edge_fn.p, ctx->lam_weight.p);
     int rc = tree_pass(ctx, false);
     if (rc) return rc;
@@ -1661,8 +1659,8 @@ int nxfx_pc_apply_begin(nxfx_ctx* ctx, const double* r, double* buf) {
   if (ctx->N == 1) {
     NXFX_LAUNCH(ctx, bif_rhs_n1_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->cur->cell_rh.p, ctx->lam_weight.p);
   } else {
-    NXFX_LAUNCH(ctx, edge_condense_kernel, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cur->cell_rh.p, r, ctx->edge_c.p, ctx->edge_fn.p);
-    NXFX_LAUNCH(ctx, bif_rhs_kernel, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->edge_g.p, ctx->edge_c.p,
+    NXFX_LAUNCH(ctx, edge_condense_kernel<false>, (int)cdiv(ctx->E, kThreads), kThreads, 0, g, ctx->cur->cell_rh.p, r, ctx->edge_c.p, ctx->edge_fn.p);
+    NXFX_LAUNCH(ctx, bif_rhs_kernel<false>, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, r, ctx->edge_g.p, ctx->edge_c.p,
                 ctx->edge_fn.p, ctx->lam_weight.p);
   }
   if (nb > 0) NXFX_LAUNCH(ctx, tree_solve_kernel<kTreeUp>, nb, kTreeThreads, tree_smem_bytes(ctx->tree.cap), t, nb, ctx->ticket.p + 1, 0);

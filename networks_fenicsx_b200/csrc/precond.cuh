@@ -1143,30 +1143,38 @@ tree_top_fs_kernel(TreeDev t, int top_chunk, double* buf, FusedN1 fin) {
 }
 
 // Edge condensation: c_e = sum r_q - w.F,  F_N = sum r_p
+// WITH_G (fresh matrix + direct solve): also the conductance g_e = 1 / sum_j R_j h_j of edge_conductance_kernel,
+// from the same pass over R h (same sum, same order)
+template <bool WITH_G = false>
 __global__ void __launch_bounds__(kThreads)
 edge_condense_kernel(Net g, const double* __restrict__ cell_rh, const double* __restrict__ r,
-                     double* __restrict__ edge_c, double* __restrict__ edge_fn) {
+                     double* __restrict__ edge_c, double* __restrict__ edge_fn, double* __restrict__ edge_g = nullptr) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= g.E) return;
   const int N = g.N;
   const double* rq = r + (size_t)g.edge_slot[e] * (N + 1);
   const double* rp = r + g.poff + (size_t)e * N;
   const double* rh = cell_rh + (size_t)e * N;
-  double s = 0.0, F = 0.0, wF = 0.0, hl = 0.0;
+  double s = 0.0, F = 0.0, wF = 0.0, hl = 0.0, W = 0.0;
   for (int a = 0; a <= N; ++a) {
     s += rq[a];
     const double hr = a < N ? rh[a] : 0.0;
+    if (WITH_G) W += hr;
     wF += 0.5 * (hl + hr) * F;
     if (a < N) F += rp[a];
     hl = hr;
   }
   edge_c[e] = s - wF;
   edge_fn[e] = F;
+  if (WITH_G) edge_g[e] = 1.0 / W;
 }
 
 // rhs_b = -r_lam + sum_in (F_N + g c) - sum_out g c      (schedule order)
 // lam_weight (multi-GPU): 0 on the ranks that hold a replicated multiplier without owning it, so
 // that -r_lambda is counted once in the all-reduced right-hand side; null = all ones.
+// WITH_DIAG (fresh matrix + direct solve): also the Laplacian diagonal and the link conductance of
+// bif_diag_kernel, from the same pass over the incidences
+template <bool WITH_DIAG = false>
 __global__ void __launch_bounds__(kThreads)
 bif_rhs_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* __restrict__ edge_g,
                const double* __restrict__ edge_c, const double* __restrict__ edge_fn,
@@ -1174,12 +1182,21 @@ bif_rhs_kernel(Net g, TreeDev t, const double* __restrict__ r, const double* __r
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n_bif) return;
   double s = lam_weight ? -lam_weight[i] * r[g.loff + i] : -r[g.loff + i];
+  double d = 0.0;
   for (int k = g.bif_ptr[i]; k < g.bif_ptr[i + 1]; ++k) {
     const int inc = g.bif_inc[k], e = inc >> 1;
-    const double gc = edge_g[e] * edge_c[e];
+    const double ge = edge_g[e];
+    const double gc = ge * edge_c[e];
     s += (inc & 1) ? (edge_fn[e] + gc) : -gc;
+    if (WITH_DIAG) d += ge;
   }
-  t.r[t.t_of_bif[i]] = s;
+  const int n = t.t_of_bif[i];
+  t.r[n] = s;
+  if (WITH_DIAG) {
+    t.diag0[n] = d;
+    const int pe = t.t_pedge[n];
+    t.tg[n] = pe >= 0 ? edge_g[pe] : 0.0;
+  }
 }
 
 // Back-substitution: q_a = q_0 + F_a ; p_0 = r_q0 + lam_u - (Mq)_0 ; p_a = p_{a-1} + r_qa - (Mq)_a
