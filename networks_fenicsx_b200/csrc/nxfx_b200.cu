@@ -4,6 +4,8 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 
@@ -658,6 +660,23 @@ int ensure_work(nxfx_ctx* ctx, size_t nvec) {
   return NXFX_OK;
 }
 
+// sentinel of the norm words the residual kernel stores into mapped pinned memory (a NaN payload no sum of squares has)
+inline double kNormSentinel() {
+  const uint64_t bits = 0x7FF8DEADBEEF0001ull;
+  double d;
+  std::memcpy(&d, &bits, sizeof d);
+  return d;
+}
+inline bool is_norm_sentinel(double v) {
+  uint64_t bits;
+  std::memcpy(&bits, &v, sizeof bits);
+  return bits == 0x7FF8DEADBEEF0001ull;
+}
+bool poll_norms_enabled() {  // NXFX_POLL_NORMS=0: always cudaStreamSynchronize (A/B measurements)
+  static const bool on = [] { const char* e = std::getenv("NXFX_POLL_NORMS"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 void push_history(nxfx_solve_info* info, double v) {
   if (info->history_len < NXFX_HISTORY_LEN) info->history[info->history_len++] = v;
 }
@@ -700,8 +719,23 @@ int solve_preonly(nxfx_ctx* ctx, const double* b, double* x, const nxfx_solve_op
     // Only the norms are needed for the decision: the residual vector itself is written (by a second
     // pass, bit-identical) only if a correction follows -- never on trees.
     const bool lazy = ctx->pipe_ok;
+    // the norms land in mapped pinned memory: the host watches the two words change instead of asking the driver
+    // to synchronise the stream (the stream-ordered work that follows needs no host-side completion); a genuine
+    // result equal to the sentinel, a faulting kernel or a long solve fall through to the synchronisation
+    volatile double* nh = ctx->scal_h;
+    const bool poll = poll_norms_enabled();
+    if (poll) { ctx->scal_h[0] = kNormSentinel(); ctx->scal_h[1] = kNormSentinel(); }
     if ((rc = do_residual(ctx, b, x, lazy ? nullptr : r, ctx->scal_h_dev, true))) return rc;
-    NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bool arrived = false;
+    if (poll) {
+      const auto t0 = std::chrono::steady_clock::now();
+      for (unsigned spin = 0;; ++spin) {
+        if (!is_norm_sentinel(nh[0]) && !is_norm_sentinel(nh[1])) { arrived = true; break; }
+        if ((spin & 255u) == 255u && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(1500)) break;
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (!arrived) NXFX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     info->rhs_norm = std::sqrt(ctx->scal_h[1]);
     info->residual_norm = std::sqrt(ctx->scal_h[0]);
     push_history(info, info->residual_norm);
