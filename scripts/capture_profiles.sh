@@ -1,3 +1,5 @@
+# Single-GPU capture recipe of the round (run under gpurun): bench line, reference arm, ncu launch list, ncu --set full of the
+# in-step kernels and of one higher-order step.  Summaries: profiles/summarize_ncu.py, profiles/make_traffic.py.
 set -x
 python bench.py --steps 20 --warmup 5 2>gpurun_out/r2_bench_n1_final.err > gpurun_out/r2_bench_n1_final.json; cut -c1-200 gpurun_out/r2_bench_n1_final.json
 python bench.py --impl reference --steps 1 --warmup 0 2>gpurun_out/r2_bench_ref.err > gpurun_out/r2_bench_ref.json; cut -c1-300 gpurun_out/r2_bench_ref.json
