@@ -50,6 +50,34 @@ def test_native_greedy_colouring_on_long_chains():
         assert np.array_equal(col, plain(E + 1, edges))
 
 
+def test_boundary_vertex_runs_for_the_pbc_upload():
+    """compute_forms uploads only the contiguous runs of boundary vertex ids (the forms read p_bc nowhere else,
+    assembly.py:258-260); scattered boundary ids fall back to the full array."""
+    from networks_fenicsx_b200.assembly import HydraulicNetworkAssembler
+
+    def runs_of(nm):
+        asm = HydraulicNetworkAssembler.__new__(HydraulicNetworkAssembler)
+        asm._network_mesh = nm
+        return asm._boundary_runs()
+
+    nm = nxfx.NetworkMesh(ng.make_tree(8, 8, 8, as_arrays=True), N=1, color_strategy="smallest_last")
+    runs = runs_of(nm)
+    assert runs == [(0, 1), (128, 256)]
+    covered = np.concatenate([np.arange(a, b) for a, b in runs])
+    assert np.array_equal(covered, np.sort(nm.boundary_values))
+    assert runs_of(nxfx.NetworkMesh(helpers.random_tree(80, 5), N=2, color_strategy="smallest_last")) is None
+
+
+def test_bench_colouring_note_follows_the_mesh_thresholds():
+    import bench
+    from networks_fenicsx_b200 import mesh as nxmesh
+
+    assert "reference's own call" in bench.colouring_note(nxmesh.NETWORKX_COLORING_MAX_EDGES, 1)
+    assert "networkx-identical" in bench.colouring_note(nxmesh.NETWORKX_COLORING_MAX_EDGES + 1, 1)
+    assert "sub-network" in bench.colouring_note(1_048_575, 8)
+    assert "native greedy" in bench.colouring_note(nxmesh.NETWORKX_IDENTICAL_MAX_EDGES + 1, 1)
+
+
 def test_tree_edges_matches_reference_generator():
     """network_generation.py:18-38 restated literally (parent stack) against the closed form."""
     def literal(n, r):
