@@ -6,7 +6,7 @@ workload ``tree``: ``make_tree(n, n, n)``, R = 1, f = 0 (demo_perf.py); ``arteri
 ``make_arterial_tree(n)`` with the radius-dependent resistance R_e = 8 mu / (pi r_e^4) from the graph's
 ``radius`` attribute and a source term f != 0 (BASELINE configs[3], demo_arterial_tree.py:16-27).
 exchange ``peer`` (in-kernel NVLink exchange, N == 1), ``nccl`` (split phases around all-reduces) or
-``auto``.  Every rank solves its part; rank 0 gathers the solution and compares it with the CPU
+``auto``.  ``NXFX_DIST_ONE_GPU=1``: all ranks share cuda:0 and reduce through gloo (single-GPU boxes).  Every rank solves its part; rank 0 gathers the solution and compares it with the CPU
 oracle's direct solve of the WHOLE network (bar: 1e-8 relative L2, BASELINE north_star)."""
 import os
 import sys
@@ -41,8 +41,16 @@ def main():
     workload = sys.argv[4] if len(sys.argv) > 4 else "tree"
     exchange = sys.argv[5] if len(sys.argv) > 5 else "auto"
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if os.environ.get("NXFX_DIST_ONE_GPU") == "1":
+        # every rank on cuda:0 (time-sliced contexts), collectives through gloo: the partition, the split-phase
+        # kernels and the host-driven all-reduces of the partitioned solve on a single-GPU box (NCCL refuses two
+        # ranks on one device; the in-kernel peer exchange would spin against a kernel that is not running)
+        local_rank, exchange = 0, "nccl"
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rank, world = dist.get_rank(), dist.get_world_size()
     G, p_bc, R, f = build_workload(workload, n, N)
     ds = DistributedSolver(G, N, p_bc, R=R, f=f, device=local_rank, chunk_nodes=chunk, exchange=exchange)

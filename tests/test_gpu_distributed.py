@@ -1,5 +1,6 @@
 """Multi-GPU parity: one tree cut over 2 GPUs, gathered solution vs the oracle's direct solve of
-the whole network (tests/dist_check.py under torchrun).  Skipped on single-GPU boxes."""
+the whole network (tests/dist_check.py under torchrun).  The 2-GPU cases are skipped on single-GPU boxes; the
+one-GPU cases run the same partition and the split-phase kernels with both ranks on cuda:0 and gloo collectives."""
 
 import pathlib
 import subprocess
@@ -27,5 +28,23 @@ def test_single_tree_partition_two_gpus(args):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29631", str(ROOT / "tests" / "dist_check.py"), *args]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "-> OK" in out.stdout
+
+
+@pytest.mark.parametrize("args,world", [
+    (("11", "1", "64", "tree", "nccl"), 2),
+    (("8", "4", "32", "arterial", "nccl"), 2),
+    (("10", "1", "32", "arterial", "nccl"), 4),
+])
+def test_single_tree_partition_ranks_sharing_one_gpu(args, world):
+    """Distributed parity that a single-GPU box can run: ``world`` ranks on cuda:0, host-driven exchange over
+    gloo; the gathered solution against the oracle's direct solve of the whole network."""
+    import os
+
+    env = dict(os.environ, NXFX_DIST_ONE_GPU="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29641", str(ROOT / "tests" / "dist_check.py"), *args]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "-> OK" in out.stdout
