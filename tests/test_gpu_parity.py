@@ -415,6 +415,52 @@ def test_higher_order_direct_solve_at_size(fd, pd, n):
     assert np.linalg.norm(r) <= 1e-12 * np.linalg.norm(solver.b.array_r)
 
 
+def test_condensation_tables_are_validated():
+    """nxfx_set_condensation rejects tables that do not fit the network (bad bandwidth, entries outside the local
+    block, unknown kinds) instead of factorising garbage; without the tables a direct solve is refused loudly."""
+    import ctypes as C
+
+    from networks_fenicsx_b200 import _lib
+    from networks_fenicsx_b200.condense import build_condensation
+
+    nm = nxfx.NetworkMesh(ng.make_tree(4, 1, 1), N=2, color_strategy="smallest_last")
+    asm = nxfx.HydraulicNetworkAssembler(nm, flux_degree=2, pressure_degree=1)
+    asm.compute_forms(p_bc_ex=P_Y)
+    solver = nxfx.Solver(asm)
+    solver.assemble()
+    cd = build_condensation(nm, 2, 1)
+    t = cd.packed()
+    c32 = lambda a: _lib.as_i32p(np.ascontiguousarray(a, dtype=np.int32))  # noqa: E731
+    c64 = lambda a: _lib.as_f64p(np.ascontiguousarray(a, dtype=np.float64))  # noqa: E731
+
+    def call(kl=cd.kl, n_max=cd.n_max, **over):
+        a = {**t, **over}
+        nm.device.call(
+            "nxfx_set_condensation", 1, cd.fd * cd.N + 1, n_max, kl, cd.pcell_base, cd.pcell_stride, c32(a["type_n"]),
+            c32(a["loc_ptr"]), c32(a["loc_kind"]), c32(a["loc_off"]), c32(a["k_ptr"]), c32(a["k_row"]), c32(a["k_col"]),
+            c32(a["k_cell"]), c64(a["k_coef"]), c32(a["c_ptr"]), c32(a["c_row"]), c32(a["c_slot"]), c64(a["c_coef"]),
+            c32(a["d_ptr"]), c32(a["d_slot"]), c32(a["d_col"]), c64(a["d_coef"]), c32(cd.bif_node))
+
+    with pytest.raises(RuntimeError, match="K entry"):
+        call(kl=1)  # entries outside the declared band
+    with pytest.raises(RuntimeError, match="bad type_n"):
+        call(n_max=cd.n_max - 1)
+    bad_kind = t["loc_kind"].copy()
+    bad_kind[0] = 9
+    with pytest.raises(RuntimeError, match="unknown kind"):
+        call(loc_kind=bad_kind)
+    bad_slot = t["c_slot"].copy()
+    bad_slot[0] = 4
+    with pytest.raises(RuntimeError, match="C entry"):
+        call(c_slot=bad_slot)
+    # the failed calls left the context without tables: a direct solve says so
+    with pytest.raises(RuntimeError, match="nxfx_set_condensation"):
+        solver.solve()
+    call()  # the right tables again
+    x = np.concatenate([fn.x.array for fn in solver.solve()])
+    assert np.isfinite(x).all() and solver.ksp.getIterationNumber() == 1
+
+
 def test_higher_order_long_edges():
     """40 cells per edge (the arterial demo's refinement): the per-edge band no longer fits the shared-memory
     variant of the LU, the global-memory variant takes over; same direct solve."""
