@@ -397,7 +397,9 @@ def load_traffic(n_dofs):
     try:
         with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as fh:
             tj = json.load(fh)
-        if tj["n_dofs_per_gpu"] == n_dofs:
+        # (a rank of a partitioned weak-scaling run holds the same subtree plus a handful of replicated
+        # multipliers: the per-GPU kernels move the same bytes to within that handful)
+        if abs(tj["n_dofs_per_gpu"] - n_dofs) <= 64:
             return tj
     except (OSError, KeyError, ValueError):
         pass
