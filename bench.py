@@ -183,15 +183,22 @@ class Problem:
                       C.byref(self.opts), C.byref(self.info))
 
     def timed_steps(self, steps, warmup, barrier, dist, torch):
+        import gc
+
         for _ in range(warmup):
             self.step()
         barrier()
-        l0 = self.dev.launch_count
-        self.dev.timer_start()
-        for _ in range(steps):
-            self.step()
-        ms = self.dev.timer_stop()
-        launches = self.dev.launch_count - l0
+        gc.collect()
+        gc.disable()  # a collection pause on one rank stalls every rank at the next exchange point
+        try:
+            l0 = self.dev.launch_count
+            self.dev.timer_start()
+            for _ in range(steps):
+                self.step()
+            ms = self.dev.timer_stop()
+            launches = self.dev.launch_count - l0
+        finally:
+            gc.enable()
         barrier()
         if dist is not None:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
