@@ -86,18 +86,17 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        # nvidia-smi loops on its own and writes to a file that is parsed afterwards: no reader thread competes with
+        # the timed loop for the interpreter lock (a stalled rank stalls every rank at the next exchange point)
+        import tempfile
+
         try:
+            self.out = tempfile.TemporaryFile(mode="w+")
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+                stdout=self.out, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self):
         if self.proc is None:
@@ -108,6 +107,9 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        self.out.seek(0)
+        self.lines = [ln.strip() for ln in self.out.read().splitlines()]
+        self.out.close()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
