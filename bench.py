@@ -28,7 +28,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
