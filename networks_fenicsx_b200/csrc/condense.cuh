@@ -188,6 +188,131 @@ cond_factor_kernel(Net g, CondDev c, const double* __restrict__ cell_rh) {
   for (int k = 0; k < 16; ++k) c.S[(size_t)k * E + e] = S[k];
 }
 
+// The same factorisation with G lanes per edge (G = 8, 16 or 32; 256 / G edges per block), band, Y_e and pivots of
+// the edge in shared memory.  Every lane of a group follows the same control flow -- the pivot search is done
+// redundantly by all of them from the same shared-memory column (a broadcast) -- and the row swap, the scaling and
+// the rank-1 update of a step are spread over the lanes, separated by __syncwarp().  The four columns of Y_e are
+// solved at once (lane = column + 4 * helper; the helpers share the inner updates).  Same operations on the same
+// operands as cond_band_lu / cond_band_solve (checked phase by phase, including read / write hazards between
+// lanes, by a lock-step emulation on the host): identical pivots and factors.  Against the thread-per-edge kernel
+// this keeps ~768 threads per SM busy on ~100 edges instead of 128 threads on 128 edges (shared memory) or an L2
+// round trip per operand (global memory).
+__host__ __device__ constexpr int cond_group_smem_doubles(int ldab, int n_max) {
+  return ((ldab + 4) * n_max + (n_max + 1) / 2) | 1;  // band, 4 columns of Y, pivots (ints); odd: spreads the banks
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+cond_factor_group_kernel(Net g, CondDev c, const double* __restrict__ cell_rh) {
+  extern __shared__ __align__(16) double cond_sm[];
+  constexpr int EPB = 256 / G, H = G / 4;
+  const int lane = threadIdx.x % G, grp = threadIdx.x / G;
+  const int e_raw = blockIdx.x * EPB + grp;
+  const bool valid = e_raw < g.E;  // a group beyond the last edge repeats it without storing: uniform control flow
+  const int e = valid ? e_raw : g.E - 1;
+  const size_t E = (size_t)g.E;
+  const EdgeInfo ei = cond_edge(g, c, e);
+  const int n = ei.n, n_max = c.n_max, kl = c.kl, kv = c.kv;
+  double* __restrict__ Bd = cond_sm + (size_t)grp * cond_group_smem_doubles(c.ldab, n_max);
+  double* __restrict__ Yb = Bd + c.ldab * n_max;
+  int* __restrict__ piv = reinterpret_cast<int*>(Yb + 4 * n_max);
+  auto A = [&](int i, int j) -> double& { return Bd[(kv + i - j) * n_max + j]; };
+  for (int k = lane; k < (c.ldab + 4) * n_max; k += G) Bd[k] = 0.0;
+  __syncwarp();
+  // at most two entries per position (adjacent cells): their sum does not depend on the order they arrive in
+  for (int k = c.k_ptr[ei.type] + lane; k < c.k_ptr[ei.type + 1]; k += G) {
+    const int cell = c.k_cell[k];
+    atomicAdd(&A(c.k_row[k], c.k_col[k]), cell >= 0 ? c.k_coef[k] * cell_rh[(size_t)e * g.N + cell] : c.k_coef[k]);
+  }
+  for (int k = c.c_ptr[ei.type] + lane; k < c.c_ptr[ei.type + 1]; k += G)
+    atomicAdd(&Yb[c.c_slot[k] * n_max + c.c_row[k]], c.c_coef[k]);
+  __syncwarp();
+  // ---- LU (dgbtf2), one elimination step per iteration ----
+  int ju = 0;
+  for (int j = 0; j < n_max; ++j) {
+    const bool act = j < n;
+    int km = 0, jp = 0;
+    if (act) {
+      km = min(kl, n - 1 - j);
+      double best = fabs(A(j, j));
+      for (int i = 1; i <= km; ++i) {
+        const double a = fabs(A(j + i, j));
+        if (a > best) { best = a; jp = i; }
+      }
+      ju = max(ju, min(j + jp + kl, n - 1));
+      if (lane == 0) {
+        piv[j] = j + jp;
+        if (valid) c.ipiv[(size_t)j * E + e] = j + jp;
+      }
+    }
+    __syncwarp();  // every lane has read the column before the swap moves it
+    if (act && jp != 0)
+      for (int col = j + lane; col <= ju; col += G) {
+        const double t = A(j, col);
+        A(j, col) = A(j + jp, col);
+        A(j + jp, col) = t;
+      }
+    __syncwarp();
+    if (act) {
+      const double inv = 1.0 / A(j, j);
+      for (int i = 1 + lane; i <= km; i += G) A(j + i, j) *= inv;
+    }
+    __syncwarp();
+    if (act) {
+      const int total = km * (ju - j);
+      for (int idx = lane; idx < total; idx += G) {
+        const int i = 1 + idx % km, col = j + 1 + idx / km;
+        A(j + i, col) -= A(j + i, j) * A(j, col);
+      }
+    }
+    __syncwarp();
+  }
+  // ---- Y = K^{-1} C: the four columns at once ----
+  const int s = lane & 3, h = lane >> 2;
+  const bool col_on = ((s < 2 ? ei.lu : ei.lv) >= 0) && ((s & 1) || c.cont);
+  double* __restrict__ y = Yb + s * n_max;
+  for (int j = 0; j < n_max; ++j) {
+    const bool act = j < n && col_on;
+    int l = j;
+    double bj = 0.0, tj = 0.0;
+    if (act) { l = piv[j]; bj = y[l]; tj = y[j]; }
+    __syncwarp();
+    if (act && h == 0 && l != j) { y[l] = tj; y[j] = bj; }
+    __syncwarp();
+    if (act && bj != 0.0) {
+      const int lm = min(kl, n - 1 - j);
+      for (int i = 1 + h; i <= lm; i += H) y[j + i] -= A(j + i, j) * bj;
+    }
+    __syncwarp();
+  }
+  for (int j = n_max - 1; j >= 0; --j) {
+    const bool act = j < n && col_on;
+    double bj = 0.0;
+    if (act) bj = y[j] / A(j, j);
+    __syncwarp();
+    if (act) {
+      if (h == 0) y[j] = bj;
+      if (bj != 0.0)
+        for (int i = max(0, j - kv) + h; i < j; i += H) y[i] -= A(i, j) * bj;
+    }
+    __syncwarp();
+  }
+  // ---- S = -D Y, factors and Y to global memory (edge-fastest: the groups of a warp fill whole sectors) ----
+  for (int idx = lane; idx < 16; idx += G) {
+    const int a = idx >> 2, sc = idx & 3;
+    double acc = 0.0;
+    for (int k = c.d_ptr[ei.type]; k < c.d_ptr[ei.type + 1]; ++k)
+      if (c.d_slot[k] == a) acc -= c.d_coef[k] * Yb[sc * n_max + c.d_col[k]];
+    if (valid) c.S[(size_t)idx * E + e] = acc;
+  }
+  if (valid) {
+    for (int k = lane; k < c.ldab * n_max; k += G)
+      if (k % n_max < n) c.band[(size_t)k * E + e] = Bd[k];
+    for (int k = lane; k < 4 * n_max; k += G)
+      if (k % n_max < n) c.Y[(size_t)k * E + e] = Yb[k];
+  }
+}
+
 // y0 = K_e^{-1} r_loc, h_e = D_e y0 (SMEM: the right-hand side is solved in shared memory -- n_max doubles per
 // thread, full occupancy; 298 instead of 335 us for P2/P1 at 524 k edges)
 template <bool SMEM>

@@ -415,6 +415,18 @@ bool cond_smem_enabled() {  // NXFX_COND_SMEM=0: global-memory variants only (A/
   static const bool on = [] { const char* e = std::getenv("NXFX_COND_SMEM"); return !(e && e[0] == '0'); }();
   return on;
 }
+// lanes per edge of the cooperative factorisation: the fewest that leave room for three blocks per SM, else the
+// fewest that fit at all; 0 = the edge's block does not fit shared memory even with one warp per edge
+int cond_group_lanes(const nxfx_ctx* ctx) {
+  static const bool on = [] { const char* e = std::getenv("NXFX_COND_GROUP"); return !(e && e[0] == '0'); }();
+  if (!on) return 0;
+  const size_t per_edge = (size_t)cond_group_smem_doubles(3 * ctx->cond.kl + 1, ctx->cond.n_max) * sizeof(double);
+  for (int G : {8, 16, 32})
+    if ((256 / G) * per_edge <= 72 * 1024) return G;
+  for (int G : {8, 16, 32})
+    if ((256 / G) * per_edge <= kCondSmemMax) return G;
+  return 0;
+}
 int cond_rhs_threads(const nxfx_ctx* ctx) {
   if (!cond_smem_enabled()) return 0;
   const size_t t = std::min<size_t>(kCondThreads, kCondSmemMax / ((size_t)ctx->cond.n_max * sizeof(double))) & ~(size_t)31;
@@ -426,7 +438,14 @@ int do_cond_setup(nxfx_ctx* ctx) {
   NXFX_REQUIRE(ctx, ctx->tree.set, "nxfx_set_tree_schedule has not been called");
   Net g = make_net(ctx);
   CondDev c = make_cond(ctx);
-  NXFX_LAUNCH(ctx, cond_factor_kernel, (int)cdiv(ctx->E, kCondThreads), kCondThreads, 0, g, c, ctx->cur->cell_rh.p);
+  // G lanes per edge with the band in shared memory when an edge's block fits; else one thread per edge out of
+  // global memory (very long edges).  NXFX_COND_GROUP=0 forces the latter (A/B measurements).
+  const int G = cond_group_lanes(ctx);
+  const size_t gsm = (size_t)cond_group_smem_doubles(c.ldab, c.n_max) * sizeof(double);
+  if (G == 8) NXFX_LAUNCH(ctx, cond_factor_group_kernel<8>, (int)cdiv(ctx->E, 32), 256, 32 * gsm, g, c, ctx->cur->cell_rh.p);
+  else if (G == 16) NXFX_LAUNCH(ctx, cond_factor_group_kernel<16>, (int)cdiv(ctx->E, 16), 256, 16 * gsm, g, c, ctx->cur->cell_rh.p);
+  else if (G == 32) NXFX_LAUNCH(ctx, cond_factor_group_kernel<32>, (int)cdiv(ctx->E, 8), 256, 8 * gsm, g, c, ctx->cur->cell_rh.p);
+  else NXFX_LAUNCH(ctx, cond_factor_kernel, (int)cdiv(ctx->E, kCondThreads), kCondThreads, 0, g, c, ctx->cur->cell_rh.p);
   if (ctx->n_bif > 0) {
     TreeDev t = make_tree(ctx);
     NXFX_LAUNCH(ctx, cond_node_kernel<true>, (int)cdiv(ctx->n_bif, kThreads), kThreads, 0, g, t, c, nullptr);
@@ -1598,6 +1617,9 @@ int nxfx_set_condensation(nxfx_ctx* ctx, int32_t continuous_pressure, int32_t fl
   k.n_max = n_max; k.kl = kl; k.per_edge = flux_dofs_per_edge; k.pcell_base = pcell_base; k.pcell_stride = pcell_stride;
   k.cont = continuous_pressure ? 1 : 0;
   NXFX_CUDA(ctx, cudaFuncSetAttribute(cond_edge_rhs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCondSmemMax));
+  NXFX_CUDA(ctx, cudaFuncSetAttribute(cond_factor_group_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCondSmemMax));
+  NXFX_CUDA(ctx, cudaFuncSetAttribute(cond_factor_group_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCondSmemMax));
+  NXFX_CUDA(ctx, cudaFuncSetAttribute(cond_factor_group_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCondSmemMax));
   const size_t Es = (size_t)E, nb = (size_t)std::max(ctx->n_bif, 1);
   NXFX_CUDA(ctx, k.band.alloc((size_t)(3 * kl + 1) * n_max * Es));
   NXFX_CUDA(ctx, k.ipiv.alloc((size_t)n_max * Es));
