@@ -194,7 +194,8 @@ cond_factor_kernel(Net g, CondDev c, const double* __restrict__ cell_rh) {
 // the rank-1 update of a step are spread over the lanes, separated by __syncwarp().  The four columns of Y_e are
 // solved at once (lane = column + 4 * helper; the helpers share the inner updates).  Same operations on the same
 // operands as cond_band_lu / cond_band_solve (checked phase by phase, including read / write hazards between
-// lanes, by a lock-step emulation on the host): identical pivots and factors.  Against the thread-per-edge kernel
+// lanes, by the lock-step emulation in tests/test_condensation_lockstep.py):
+// identical pivots and factors.  Against the thread-per-edge kernel
 // this keeps ~768 threads per SM busy on ~100 edges instead of 128 threads on 128 edges (shared memory) or an L2
 // round trip per operand (global memory).
 __host__ __device__ constexpr int cond_group_smem_doubles(int ldab, int n_max) {
